@@ -1,0 +1,60 @@
+// lf_oracle_capi.cpp — TEST INFRASTRUCTURE: ctypes-friendly entry points of the CPU oracle (lf_oracle.h).
+// Loaded only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+#include <cstring>
+#include <string>
+
+#include "lf_oracle.h"
+#include "scenepack.h"
+
+namespace {
+struct Handle {
+    lfpack::ScenePack pack;
+    lforacle::Oracle* oracle = nullptr;
+    ~Handle() { delete oracle; }
+};
+}
+
+extern "C" {
+
+void* lforacle_open_pack(const char* path) {
+    Handle* h = new Handle;
+    std::string err;
+    if (!lfpack::read(path, h->pack, &err)) { delete h; return nullptr; }
+    h->oracle = new lforacle::Oracle(h->pack.view(), h->pack.params(), h->pack.camera());
+    return h;
+}
+void lforacle_close(void* hv) { delete static_cast<Handle*>(hv); }
+
+void lforacle_get_params(void* hv, LfParams* p, LfCamera* c) {
+    Handle* h = static_cast<Handle*>(hv);
+    if (p) *p = h->oracle->params;
+    if (c) *c = h->oracle->camera;
+}
+void lforacle_set_params(void* hv, const LfParams* p, const LfCamera* c) {
+    Handle* h = static_cast<Handle*>(hv);
+    if (p) h->oracle->params = *p;
+    if (c) h->oracle->camera = *c;
+}
+// cull: 0 = reference behaviour (visit every pierced box), 1 = conservative distance cull
+void lforacle_set_options(void* hv, int cull, int count) {
+    Handle* h = static_cast<Handle*>(hv);
+    h->oracle->cull = cull != 0;
+    h->oracle->count = count != 0;
+}
+void lforacle_render_frames(void* hv, int first_frame, int nframes, int frame_stride, int tile_x, int tile_y, float* accum) {
+    static_cast<Handle*>(hv)->oracle->RenderFrames(first_frame, nframes, frame_stride, tile_x, tile_y, accum);
+}
+void lforacle_primary_hits(void* hv, int frame, float* t, int32_t* tri, int32_t* mat, int32_t* emitter) {
+    static_cast<Handle*>(hv)->oracle->PrimaryHits(frame, t, tri, mat, emitter);
+}
+void lforacle_sample(void* hv, int lx, int ly, int tile_x, int tile_y, int frame, float* rgb) {
+    int px, py;
+    static_cast<Handle*>(hv)->oracle->Sample(lx, ly, tile_x, tile_y, frame, rgb, &px, &py, nullptr);
+}
+void lforacle_rand_kat(int px, int py, int frame, int n, uint32_t* seedx, float* values) {
+    lforacle::Oracle::RandKat(px, py, frame, n, seedx, values);
+}
+void lforacle_get_counters(void* hv, LfCounters* out) { *out = static_cast<Handle*>(hv)->oracle->counters; }
+void lforacle_reset_counters(void* hv) { std::memset(&static_cast<Handle*>(hv)->oracle->counters, 0, sizeof(LfCounters)); }
+
+}  // extern "C"
