@@ -1,0 +1,471 @@
+// lf_kernels.cu — the CUDA kernels of the path-tracing core (sm_100a) and their launchers.
+//
+// Wavefront pipeline, one launch per stage and bounce, all counts kept on the device (no host sync):
+//   generate    renderer.glsl:25-62      pixel -> RNG seed, jittered thin-lens camera ray, path state reset
+//   extend      closest_hit.glsl         persistent warps pull 32 rays at a time from the live queue
+//   shade       pathtrace.glsl:223-291   miss/emitter/surface shading, NEE candidates, BSDF sample, RR;
+//                                        survivors and shadow requests are compacted with ballot + popc
+//   shadow      anyhit.glsl              persistent warps; radiance += (visible NEE sum) * throughput
+//   accumulate  renderer.glsl:64-68      per pixel, samples of the batch added in frame order
+// plus a one-thread-per-sample megakernel built from the same device functions (cross-check / comparison)
+// and the post-process kernel (postprocess.glsl tonemappers) used by the read-back calls.
+#include "lf_device.cuh"
+#include "lf_kernels.h"
+
+namespace lf {
+
+// ---------------------------------------------------------------------------------------------- path state
+struct PathRegs {
+    Ray ray;
+    f3 thr, rad, absn, stale;
+    float bsdf_pdf;
+    Rng rng;
+};
+struct Nee {
+    f3 origin, d0, c0, d1, c1, T;
+    float m0, m1;
+    bool has0, has1;
+};
+
+// One iteration of the bounce loop after ClosestHit (pathtrace.glsl:223-291).  Returns true when the path
+// continues with ps.ray; NEE candidates (already weighted, visibility pending) go to `nee`.
+template <bool COUNT>
+LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs& ps, const Hit& hit, Nee& nee, DevCounters* cnt) {
+    nee.has0 = nee.has1 = false;
+    const float t = hit.t;
+    const f3 rd = ps.ray.d;
+
+    if (t == kINF) {   // pathtrace.glsl:223-244
+        if (P.use_constant_bg) {
+            ps.rad = ps.rad + mk3(P.bg[0], P.bg[1], P.bg[2]) * ps.thr;
+        } else if (P.use_envmap) {
+            float misWeight = 1.0f;
+            float ux = (kPI + atan2f(rd.z, rd.x)) * (1.0f / kTWO_PI), uy = acosf(rd.y) * (1.0f / kPI);
+            if (depth > 0) {
+                float lightPdf = EnvPdf(S, P, rd);
+                misWeight = powerHeuristic(ps.bsdf_pdf, lightPdf);
+            }
+            bump<COUNT>(cnt, C_ENV_MISS);
+            ps.rad = ps.rad + misWeight * hdrLinear(S, ux, uy) * ps.thr * P.hdr_multiplier;
+        }
+        return false;
+    }
+
+    if (hit.light >= 0) {   // analytic light is the nearest hit (pathtrace.glsl:246-261 with the stale State)
+        ps.rad = ps.rad + ps.stale * ps.thr;
+        LightRec L = load_light(S, hit.light);
+        f3 Le = L.emission;
+        if (depth != 0) Le = powerHeuristic(ps.bsdf_pdf, hit.lpdf) * L.emission;   // EmitterSample, sampling.glsl:271-282
+        ps.rad = ps.rad + Le * ps.thr;
+        return false;
+    }
+
+    Surf s;
+    load_surface<COUNT>(S, hit, rd, s, cnt);
+    ps.stale = s.mat.emission;
+
+    if (dot(s.normal, s.ffnormal) > 0.0f) ps.absn = mk3(0.0f);   // :250-251
+    ps.rad = ps.rad + s.mat.emission * ps.thr;                     // :253
+    {
+        f3 a = -ps.absn * t;                                      // :264
+        ps.thr = ps.thr * mk3(expf(a.x), expf(a.y), expf(a.z));
+    }
+
+    // ---- DirectLight (pathtrace.glsl:126-204): weighted candidates now, visibility later
+    const f3 V = -rd;
+    f3 surfacePos = hit.fhp + s.normal * kEPS;
+    nee.origin = surfacePos;
+    nee.T = ps.thr;
+    if (P.use_envmap && !P.use_constant_bg) {
+        f3 color;
+        bump<COUNT>(cnt, C_ENV_NEE);
+        float4 dirPdf = EnvSample(S, P, ps.rng, color);
+        f3 lightDir = mk3(dirPdf.x, dirPdf.y, dirPdf.z);
+        float lightPdf = dirPdf.w;
+        float pdf;
+        f3 f = DisneyEval(s, V, s.ffnormal, lightDir, pdf);
+        if (pdf > 0.0f) {
+            float misWeight = powerHeuristic(lightPdf, pdf);
+            if (misWeight > 0.0f) {
+                nee.c0 = misWeight * f * fabsf(dot(lightDir, s.ffnormal)) * color / lightPdf;
+                nee.d0 = lightDir;
+                nee.m0 = kINF - kEPS;
+                nee.has0 = true;
+            }
+        }
+    }
+    if (S.num_lights > 0) {
+        int index = (int)(rnd(ps.rng) * (float)S.num_lights);
+        LightRec light = load_light(S, index);
+        LightSample ls;
+        sampleOneLight(light, S.num_lights, surfacePos, ps.rng, ls);
+        if (dot(ls.direction, ls.normal) < 0.0f) {
+            float pdf;
+            f3 f = DisneyEval(s, V, s.ffnormal, ls.direction, pdf);
+            float weight = 1.0f;
+            if (light.area > 0.0f) weight = powerHeuristic(ls.pdf, pdf);
+            if (pdf > 0.0f) {
+                nee.c1 = weight * f * fabsf(dot(s.ffnormal, ls.direction)) * ls.emission / ls.pdf;
+                nee.d1 = ls.direction;
+                nee.m1 = ls.dist - kEPS;
+                nee.has1 = true;
+            }
+        }
+    }
+
+    // ---- BSDF sample (pathtrace.glsl:268-291)
+    f3 L;
+    float pdf;
+    f3 f = DisneySample(s, V, s.ffnormal, ps.rng, L, pdf);
+    ps.bsdf_pdf = pdf;
+    if (dot(s.ffnormal, L) < 0.0f) {
+        f3 e = s.mat.extinction;
+        ps.absn = -mk3(logf(e.x), logf(e.y), logf(e.z)) / s.mat.atDistance;
+    }
+    if (pdf > 0.0f) ps.thr = ps.thr * (f * fabsf(dot(s.ffnormal, L)) / pdf);
+    else return false;
+
+    if (P.enable_rr && depth >= P.rr_depth) {
+        float q = gmin(gmax(ps.thr.x, gmax(ps.thr.y, ps.thr.z)) + 0.001f, 0.95f);
+        if (rnd(ps.rng) > q) return false;
+        ps.thr = ps.thr / q;
+    }
+    ps.ray.d = L;
+    ps.ray.o = hit.fhp + L * kEPS;
+    return true;
+}
+
+// slot -> tile-local pixel: 8x4 pixel blocks per warp so that primary rays of a warp stay coherent
+LFD bool slot_pixel(const DevParams& P, int q, int& lx, int& ly) {
+    int blk = q >> 5, i = q & 31;
+    int bw = P.pix_w8 >> 3;
+    int bx = blk % bw, by = blk / bw;
+    lx = bx * 8 + (i & 7);
+    ly = by * 4 + (i >> 3);
+    if (lx >= P.tile_w || ly >= P.tile_h) return false;
+    int px = P.tile_w * P.tile_x + lx, py = P.tile_h * P.tile_y + ly;   // viewport offset of the tile copy (TiledRenderer.cpp:342)
+    return px >= 0 && py >= 0 && px < P.width && py < P.height;
+}
+LFD int pixel_slot(const DevParams& P, int lx, int ly) {
+    int bw = P.pix_w8 >> 3;
+    return (((ly >> 2) * bw + (lx >> 3)) << 5) + ((ly & 3) << 3) + (lx & 7);
+}
+
+// warp-aggregated queue append: one atomicAdd per warp, positions by ballot prefix
+LFD void queue_push(int* queue, int* count, bool alive, int value) {
+    unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (m == 0) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+LFD void store_state(const PathSoA& A, int s, const PathRegs& ps) {
+    A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+    A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
+    A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
+    A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
+    A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
+    A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+    A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+}
+
+// ---------------------------------------------------------------------------------------------- generate
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathSoA A, Queues Q, DevCounters* cnt) {
+    int total = P.num_frames * P.slots_per_frame;                  // multiple of 32
+    int* count0 = Q.counts + 0 * Q.stride + 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+        int fi = s / P.slots_per_frame, q = s - fi * P.slots_per_frame;
+        int lx, ly;
+        bool valid = slot_pixel(P, q, lx, ly);
+        if (valid) {
+            PathRegs ps;
+            ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
+            ps.thr = mk3(1.0f); ps.rad = mk3(0.0f); ps.absn = mk3(0.0f); ps.bsdf_pdf = 0.f;
+            ps.stale = xyz(ldg4(S.materials + 1));                 // State is zero-filled: matID 0's emission (pathtrace.glsl:213,253)
+            store_state(A, s, ps);
+            bump<COUNT>(cnt, C_SAMPLES);
+        }
+        queue_push(Q.active[0], count0, valid, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- extend
+template <bool CULL, bool COUNT, int STACK>
+__global__ void __launch_bounds__(kBlockThreads) k_extend(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
+                                                        int* cursor, DevCounters* cnt) {
+    __shared__ int stack[STACK * kBlockThreads];
+    int* stk = stack + threadIdx.x;
+    const int count = *countp;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        int i = base + lane;
+        if (i < count) {
+            int s = queue[i];
+            Ray r; r.o = xyz(A.ray_o[s]); r.d = xyz(A.ray_d[s]);
+            Hit h;
+            trace<false, CULL, COUNT>(S, r, 0.f, h, stk, cnt);
+            A.hit_f[s] = make_float4(h.t, h.u, h.v, h.lpdf);
+            A.hit_i[s] = make_int4(h.tri, h.inst, h.light, h.mat);
+            A.hit_p[s] = make_float4(h.fhp.x, h.fhp.y, h.fhp.z, 0.f);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- shade
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shade(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
+    const int* queue = Q.active[depth & 1];
+    int* next = Q.active[(depth + 1) & 1];
+    const int count = Q.counts[0 * Q.stride + depth];
+    int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
+    int* shadowCount = Q.counts + 1 * Q.stride + depth;
+    const int rounded = (count + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool alive = false, wantShadow = false;
+        int s = -1;
+        if (i < count) {
+            s = queue[i];
+            PathRegs ps;
+            float4 o = A.ray_o[s], d = A.ray_d[s], th = A.thr[s], ra = A.rad[s], ab = A.absn[s], st = A.stale[s];
+            uint4 g = A.rng[s];
+            ps.ray.o = xyz(o); ps.ray.d = xyz(d); ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab); ps.stale = xyz(st);
+            ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
+            Hit h;
+            float4 hf = A.hit_f[s]; int4 hi = A.hit_i[s]; float4 hp = A.hit_p[s];
+            h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w; h.fhp = xyz(hp);
+            Nee nee;
+            alive = shade_bounce<COUNT>(S, P, depth, ps, h, nee, cnt);
+            alive = alive && (depth + 1 < P.max_depth);
+            wantShadow = nee.has0 || nee.has1;
+            if (wantShadow) {
+                A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
+                if (nee.has0) { A.sh_d0[s] = make_float4(nee.d0.x, nee.d0.y, nee.d0.z, nee.m0); A.sh_c0[s] = make_float4(nee.c0.x, nee.c0.y, nee.c0.z, 0.f); }
+                if (nee.has1) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
+                A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);
+            } else if (h.t != kINF && h.light < 0) {
+                ps.rad = ps.rad + mk3(0.0f) * nee.T;              // radiance += DirectLight() * throughput with Li == 0 (pathtrace.glsl:266)
+            }
+            store_state(A, s, ps);
+        }
+        queue_push(next, nextCount, alive, s);
+        queue_push(Q.shadow, shadowCount, wantShadow, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- shadow
+template <bool CULL, bool COUNT, int STACK>
+__global__ void __launch_bounds__(kBlockThreads) k_shadow(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
+                                                        int* cursor, DevCounters* cnt) {
+    __shared__ int stack[STACK * kBlockThreads];
+    int* stk = stack + threadIdx.x;
+    const int count = *countp;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        int i = base + lane;
+        if (i < count) {
+            int s = queue[i];
+            float4 so = A.sh_o[s];
+            int mask = __float_as_int(so.w);
+            Ray r; r.o = xyz(so);
+            Hit dummy;
+            f3 Li = mk3(0.0f);
+            if (mask & 1) {
+                float4 d0 = A.sh_d0[s];
+                r.d = xyz(d0);
+                if (!trace<true, CULL, COUNT>(S, r, d0.w, dummy, stk, cnt)) Li = Li + xyz(A.sh_c0[s]);
+            }
+            if (mask & 2) {
+                float4 d1 = A.sh_d1[s];
+                r.d = xyz(d1);
+                if (!trace<true, CULL, COUNT>(S, r, d1.w, dummy, stk, cnt)) Li = Li + xyz(A.sh_c1[s]);
+            }
+            float4 ra = A.rad[s];
+            f3 rad = xyz(ra) + Li * xyz(A.sh_T[s]);              // radiance += DirectLight(r, state) * throughput
+            A.rad[s] = make_float4(rad.x, rad.y, rad.z, 0.f);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- accumulate
+// color = pixelColor + accumColor (renderer.glsl:68), one add per frame of the batch, in frame order.
+__global__ void __launch_bounds__(256) k_accumulate(DevParams P, PathSoA A, float* __restrict__ accum) {
+    int n = P.tile_w * P.tile_h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int lx = i % P.tile_w, ly = i / P.tile_w;
+        int px = P.tile_w * P.tile_x + lx, py = P.tile_h * P.tile_y + ly;
+        if (px >= P.width || py >= P.height) continue;
+        int q = pixel_slot(P, lx, ly);
+        float* a = accum + 3 * ((size_t)py * P.width + px);
+        float r = a[0], g = a[1], b = a[2];
+        for (int fi = 0; fi < P.num_frames; fi++) {
+            float4 c = A.rad[(size_t)fi * P.slots_per_frame + q];
+            r = c.x + r; g = c.y + g; b = c.z + b;
+        }
+        a[0] = r; a[1] = g; a[2] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- megakernel
+// The same device functions, one thread per pixel-sample for the whole path (kernel_mode = 1).
+template <bool CULL, bool COUNT, int STACK>
+__global__ void __launch_bounds__(kBlockThreads) k_megakernel(DevScene S, DevParams P, PathSoA A, DevCounters* cnt) {
+    __shared__ int stack[STACK * kBlockThreads];
+    int* stk = stack + threadIdx.x;
+    int total = P.num_frames * P.slots_per_frame;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+        int fi = s / P.slots_per_frame, q = s - fi * P.slots_per_frame;
+        int lx, ly;
+        if (!slot_pixel(P, q, lx, ly)) continue;
+        PathRegs ps;
+        ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
+        ps.thr = mk3(1.0f); ps.rad = mk3(0.0f); ps.absn = mk3(0.0f); ps.bsdf_pdf = 0.f;
+        ps.stale = xyz(ldg4(S.materials + 1));
+        bump<COUNT>(cnt, C_SAMPLES);
+        for (int depth = 0; depth < P.max_depth; depth++) {
+            Hit h;
+            trace<false, CULL, COUNT>(S, ps.ray, 0.f, h, stk, cnt);
+            Nee nee;
+            bool go = shade_bounce<COUNT>(S, P, depth, ps, h, nee, cnt);
+            if (h.t != kINF && h.light < 0) {
+                f3 Li = mk3(0.0f);
+                Ray sr; sr.o = nee.origin;
+                Hit dummy;
+                if (nee.has0) { sr.d = nee.d0; if (!trace<true, CULL, COUNT>(S, sr, nee.m0, dummy, stk, cnt)) Li = Li + nee.c0; }
+                if (nee.has1) { sr.d = nee.d1; if (!trace<true, CULL, COUNT>(S, sr, nee.m1, dummy, stk, cnt)) Li = Li + nee.c1; }
+                ps.rad = ps.rad + Li * nee.T;
+            }
+            if (!go) break;
+        }
+        A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- probes / post
+__global__ void k_export_hits(DevScene S, DevParams P, PathSoA A, float* t, int* tri, int* mat, int* emitter) {
+    int n = P.tile_w * P.tile_h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int lx = i % P.tile_w, ly = i / P.tile_w;
+        int q = pixel_slot(P, lx, ly);
+        float4 hf = A.hit_f[q]; int4 hi = A.hit_i[q];
+        size_t o = (size_t)ly * P.width + lx;
+        t[o] = hf.x;
+        tri[o] = (hi.z < 0 && hi.x >= 0) ? __ldg(S.tri_vx + hi.x) : -1;
+        mat[o] = (hi.z < 0 && hi.x >= 0) ? hi.w : -1;
+        emitter[o] = hi.z >= 0 ? 1 : 0;
+    }
+}
+
+// postprocess.glsl:26-172 without chromatic aberration / vignette: color = accum * invSampleCounter, then tonemap.
+LFD float tm_aces(float c) { return clampf((c * (2.51f * c + 0.03f)) / (c * (2.43f * c + 0.59f) + 0.14f), 0.0f, 1.0f); }
+LFD float tm_kanjero(float c, bool rgb) {
+    float v = powf((c * (c * (1.2295f * c + 0.3135f) + 1.1935f * 0.4655f) / (c * (1.1935f * c + 0.4655f) + 0.073f)), 1.7f);
+    if (rgb) v = powf(v, 1.0f / 0.8f);
+    v *= 0.8f;
+    return clampf(v, 0.0f, 1.0f);
+}
+LFD float tm_hejl(float c) { c = gmax(0.0f, c - 0.004f); return (c * (6.2f * c + .5f)) / (c * (6.2f * c + 1.7f) + 0.06f); }
+LFD float tm_uncharted(float c) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
+}
+__global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned char* out_u8, int n, float inv, int tonemap) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float c[3] = {accum[3 * i] * inv, accum[3 * i + 1] * inv, accum[3 * i + 2] * inv};
+        const float g = 1.0f / 2.2f;
+        if (tonemap == 1) {
+            float lum = 0.3f * c[0] + 0.6f * c[1] + 0.1f * c[2];
+            for (int k = 0; k < 3; k++) c[k] = powf(c[k] * 1.0f / (1.0f + lum / 2.f), g);
+        } else if (tonemap == 2) {
+            for (int k = 0; k < 3; k++) c[k] = powf(tm_aces(c[k]), g);
+        } else if (tonemap == 3) {
+            for (int k = 0; k < 3; k++) c[k] = powf(clampf(c[k] / (c[k] + 1.f), 0.0f, 1.0f), g);
+        } else if (tonemap == 4) {
+            for (int k = 0; k < 3; k++) c[k] = powf(tm_kanjero(c[k], true), g);
+        } else if (tonemap == 5) {
+            for (int k = 0; k < 3; k++) c[k] = tm_hejl(c[k]);
+        } else if (tonemap == 6) {
+            for (int k = 0; k < 3; k++) c[k] = powf(tm_uncharted(c[k]), g) * 1.75f;
+        }
+        if (out_f) { out_f[3 * i] = c[0]; out_f[3 * i + 1] = c[1]; out_f[3 * i + 2] = c[2]; }
+        if (out_u8)
+            for (int k = 0; k < 3; k++) out_u8[3 * i + k] = (unsigned char)__float2int_rn(clampf(c[k], 0.0f, 1.0f) * 255.0f);   // GL float -> unorm8
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- launchers
+template <bool CULL, bool COUNT, int STACK>
+static void launch_trace_kernels_t(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
+    if (which == 0) k_extend<CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+    else k_shadow<CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+}
+template <bool CULL, bool COUNT>
+static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
+    if (L.stack_depth <= 32) launch_trace_kernels_t<CULL, COUNT, 32>(L, which, queue, countp, cursor);
+    else launch_trace_kernels_t<CULL, COUNT, 64>(L, which, queue, countp, cursor);
+}
+static void launch_trace(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
+    if (L.cull) { if (L.count) launch_trace_kernels_s<true, true>(L, which, queue, countp, cursor); else launch_trace_kernels_s<true, false>(L, which, queue, countp, cursor); }
+    else { if (L.count) launch_trace_kernels_s<false, true>(L, which, queue, countp, cursor); else launch_trace_kernels_s<false, false>(L, which, queue, countp, cursor); }
+}
+
+void launch_generate(const LaunchCtx& L) {
+    int total = L.params.num_frames * L.params.slots_per_frame;
+    int blocks = (total + 255) / 256;
+    if (blocks > L.sm_count * 8) blocks = L.sm_count * 8;
+    if (L.count) k_generate<true><<<blocks, 256, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, L.counters);
+    else k_generate<false><<<blocks, 256, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, L.counters);
+}
+void launch_extend(const LaunchCtx& L, int depth) {
+    const Queues& Q = L.queues;
+    launch_trace(L, 0, Q.active[depth & 1], Q.counts + 0 * Q.stride + depth, Q.counts + 2 * Q.stride + depth);
+}
+void launch_shade(const LaunchCtx& L, int depth) {
+    int blocks = L.sm_count * 8;
+    if (L.count) k_shade<true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+    else k_shade<false><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+}
+void launch_shadow(const LaunchCtx& L, int depth) {
+    const Queues& Q = L.queues;
+    launch_trace(L, 1, Q.shadow, Q.counts + 1 * Q.stride + depth, Q.counts + 3 * Q.stride + depth);
+}
+void launch_accumulate(const LaunchCtx& L, float* accum) {
+    int n = L.params.tile_w * L.params.tile_h;
+    int blocks = (n + 255) / 256;
+    if (blocks > L.sm_count * 8) blocks = L.sm_count * 8;
+    k_accumulate<<<blocks, 256, 0, L.stream>>>(L.params, L.soa, accum);
+}
+template <bool CULL, bool COUNT>
+static void launch_mega_s(const LaunchCtx& L, int blocks) {
+    if (L.stack_depth <= 32) k_megakernel<CULL, COUNT, 32><<<blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.params, L.soa, L.counters);
+    else k_megakernel<CULL, COUNT, 64><<<blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.params, L.soa, L.counters);
+}
+void launch_megakernel(const LaunchCtx& L) {
+    int total = L.params.num_frames * L.params.slots_per_frame;
+    int blocks = (total + kBlockThreads - 1) / kBlockThreads;
+    if (L.cull) { if (L.count) launch_mega_s<true, true>(L, blocks); else launch_mega_s<true, false>(L, blocks); }
+    else { if (L.count) launch_mega_s<false, true>(L, blocks); else launch_mega_s<false, false>(L, blocks); }
+}
+void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* emitter) {
+    int n = L.params.tile_w * L.params.tile_h;
+    k_export_hits<<<(n + 255) / 256, 256, 0, L.stream>>>(L.scene, L.params, L.soa, t, tri, mat, emitter);
+}
+void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int npix, float inv, int tonemap) {
+    k_post<<<(npix + 255) / 256, 256, 0, stream>>>(accum, out_f, out_u8, npix, inv, tonemap);
+}
+
+}  // namespace lf

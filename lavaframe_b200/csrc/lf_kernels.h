@@ -1,0 +1,30 @@
+// lf_kernels.h — host-callable launchers of the kernels in lf_kernels.cu.
+#pragma once
+
+#include "lf_types.h"
+
+namespace lf {
+
+struct LaunchCtx {
+    DevScene     scene;
+    DevParams    params;
+    PathSoA      soa;
+    Queues       queues;
+    DevCounters* counters;
+    cudaStream_t stream;
+    int sm_count;
+    int persistent_blocks;   // CTAs of the persistent traversal kernels (multiple of the SM count)
+    int stack_depth;         // traversal stack entries the scene needs (<= 64)
+    bool cull, count;
+};
+
+void launch_generate(const LaunchCtx& L);
+void launch_extend(const LaunchCtx& L, int depth);
+void launch_shade(const LaunchCtx& L, int depth);
+void launch_shadow(const LaunchCtx& L, int depth);
+void launch_accumulate(const LaunchCtx& L, float* accum);
+void launch_megakernel(const LaunchCtx& L);
+void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* emitter);
+void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int npix, float inv, int tonemap);
+
+}  // namespace lf

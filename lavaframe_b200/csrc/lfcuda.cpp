@@ -1,0 +1,613 @@
+// lfcuda.cpp — implementation of the C ABI in include/lfcuda.h: context, scene upload + re-pack, uniform
+// handling, the wavefront launch sequence, read-backs and the NCCL sum of the accumulation buffer.
+// There is NO CPU fallback: every entry point that computes needs a CUDA device and fails loudly otherwise.
+#include "lfcuda.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "lf_kernels.h"
+#include "lf_repack.h"
+
+using namespace lf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct StageEvent { int stage; cudaEvent_t a, b; };
+
+// Minimal NCCL surface, bound at run time (torch ships its own libnccl; binding lazily lets both share it).
+struct NcclId { char b[128]; };   // ncclUniqueId, passed by value
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct lfcuda_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    // scene
+    bool have_scene = false;
+    PackedScene packed;
+    std::vector<float> host_nodes;        // reference node array (kept for lfcuda_update_instances)
+    int top_index = 0, num_tri_refs = 0;
+    DevScene dev{};
+    std::vector<void*> scene_allocs;
+    cudaArray_t tex_array = nullptr, hdr_array = nullptr;
+    float4* d_nodes = nullptr; size_t nodes_cap = 0;
+    float4* d_inst = nullptr;
+    float4* d_materials = nullptr; int materials_cap = 0;
+
+    // uniforms
+    bool have_params = false, have_camera = false;
+    LfParams params{};
+    LfCamera camera{};
+
+    // path state
+    size_t capacity = 0;                  // slots
+    int frames_cap = 0, slots_per_frame = 0, pix_w8 = 0, pix_h4 = 0;
+    std::vector<void*> state_allocs;
+    PathSoA soa{};
+    Queues queues{};
+    float* d_accum = nullptr; size_t accum_floats = 0;
+    float* d_out_f = nullptr; unsigned char* d_out_u8 = nullptr;
+    DevCounters* d_counters = nullptr;
+
+    // instrumentation
+    bool profiling = false;
+    std::vector<StageEvent> events;
+    LfStageStats stats{};
+    uint64_t launches = 0;
+
+    // NCCL
+    Nccl nccl;
+    void* comm = nullptr;
+};
+
+namespace {
+
+int fail(lfcuda_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? LFCUDA_ENOMEM : LFCUDA_ECUDA, \
+                                           "%s failed: %s", #call, cudaGetErrorString(e_));              \
+    } while (0)
+
+template <class T> int upload(lfcuda_ctx* ctx, const T* src, size_t n, T** dst, std::vector<void*>& owner) {
+    *dst = nullptr;
+    if (n == 0) return 0;
+    CK(cudaMalloc((void**)dst, n * sizeof(T)));
+    owner.push_back(*dst);
+    CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+void free_scene(lfcuda_ctx* c) {
+    for (void* p : c->scene_allocs) cudaFree(p);
+    c->scene_allocs.clear();
+    if (c->dev.tex_maps) cudaDestroyTextureObject(c->dev.tex_maps);
+    if (c->dev.hdr_tex) cudaDestroyTextureObject(c->dev.hdr_tex);
+    if (c->tex_array) cudaFreeArray(c->tex_array);
+    if (c->hdr_array) cudaFreeArray(c->hdr_array);
+    c->tex_array = c->hdr_array = nullptr;
+    c->dev = DevScene{};
+    c->have_scene = false;
+}
+
+void free_state(lfcuda_ctx* c) {
+    for (void* p : c->state_allocs) cudaFree(p);
+    c->state_allocs.clear();
+    c->capacity = 0;
+    c->d_accum = nullptr; c->d_out_f = nullptr; c->d_out_u8 = nullptr;
+}
+
+int alloc_state(lfcuda_ctx* ctx) {
+    free_state(ctx);
+    const LfParams& P = ctx->params;
+    ctx->pix_w8 = (P.tile_width + 7) / 8 * 8;
+    ctx->pix_h4 = (P.tile_height + 3) / 4 * 4;
+    ctx->slots_per_frame = ctx->pix_w8 * ctx->pix_h4;
+    int F = P.frames_in_flight;
+    if (F <= 0) {   // auto: about 4 M pixel-samples in flight, at least one frame
+        F = (int)((size_t)(4u << 20) / (size_t)ctx->slots_per_frame);
+        if (F < 1) F = 1;
+        if (F > 256) F = 256;
+    }
+    ctx->frames_cap = F;
+    size_t cap = (size_t)F * ctx->slots_per_frame;
+    auto A = [&](void** p, size_t bytes) -> int {
+        CK(cudaMalloc(p, bytes));
+        ctx->state_allocs.push_back(*p);
+        return 0;
+    };
+    float4** f4s[] = {&ctx->soa.ray_o, &ctx->soa.ray_d, &ctx->soa.hit_f, &ctx->soa.hit_p, &ctx->soa.thr, &ctx->soa.rad, &ctx->soa.absn,
+                      &ctx->soa.stale, &ctx->soa.sh_o, &ctx->soa.sh_d0, &ctx->soa.sh_c0, &ctx->soa.sh_d1, &ctx->soa.sh_c1, &ctx->soa.sh_T};
+    for (float4** p : f4s) { int r = A((void**)p, cap * sizeof(float4)); if (r) return r; }
+    int r;
+    if ((r = A((void**)&ctx->soa.hit_i, cap * sizeof(int4)))) return r;
+    if ((r = A((void**)&ctx->soa.rng, cap * sizeof(uint4)))) return r;
+    if ((r = A((void**)&ctx->queues.active[0], cap * sizeof(int)))) return r;
+    if ((r = A((void**)&ctx->queues.active[1], cap * sizeof(int)))) return r;
+    if ((r = A((void**)&ctx->queues.shadow, cap * sizeof(int)))) return r;
+    ctx->queues.stride = P.max_depth + 2;
+    if ((r = A((void**)&ctx->queues.counts, (size_t)4 * ctx->queues.stride * sizeof(int)))) return r;
+    ctx->accum_floats = (size_t)P.width * P.height * 3;
+    if ((r = A((void**)&ctx->d_accum, ctx->accum_floats * sizeof(float)))) return r;
+    if ((r = A((void**)&ctx->d_out_f, ctx->accum_floats * sizeof(float)))) return r;
+    if ((r = A((void**)&ctx->d_out_u8, ctx->accum_floats))) return r;
+    CK(cudaMemsetAsync(ctx->d_accum, 0, ctx->accum_floats * sizeof(float), ctx->stream));
+    ctx->capacity = cap;
+    return 0;
+}
+
+void fill_dev_params(const lfcuda_ctx* c, DevParams& D, int first_frame, int nframes, int stride, int tile_x, int tile_y) {
+    const LfParams& P = c->params;
+    const LfCamera& C = c->camera;
+    std::memset(&D, 0, sizeof D);
+    D.width = P.width; D.height = P.height; D.tile_w = P.tile_width; D.tile_h = P.tile_height;
+    D.max_depth = P.max_depth; D.enable_rr = P.enable_rr; D.rr_depth = P.rr_depth;
+    D.use_envmap = (P.use_envmap && c->dev.hdr_w > 0) ? 1 : 0;
+    D.use_constant_bg = P.use_constant_bg;
+    for (int k = 0; k < 3; k++) {
+        D.bg[k] = P.bg_color[k];
+        D.cam_pos[k] = C.position[k]; D.cam_right[k] = C.right[k]; D.cam_up[k] = C.up[k]; D.cam_fwd[k] = C.forward[k];
+    }
+    D.hdr_multiplier = P.hdr_multiplier;
+    D.hdr_resolution = (float)(c->dev.hdr_w * c->dev.hdr_h);          // TiledRenderer.cpp:222
+    D.inv_tiles_x = 1.0f / ((float)P.width / P.tile_width);            // TiledRenderer.cpp:226-227
+    D.inv_tiles_y = 1.0f / ((float)P.height / P.tile_height);
+    D.cam_scale = tanf(C.fov * 0.5f);                                  // renderer.glsl:51
+    D.focal_dist = C.focal_dist; D.aperture = C.aperture;
+    D.tile_x = tile_x; D.tile_y = tile_y;
+    D.first_frame = first_frame; D.frame_stride = stride; D.num_frames = nframes;
+    D.pix_w8 = c->pix_w8; D.pix_h4 = c->pix_h4; D.slots_per_frame = c->slots_per_frame;
+}
+
+struct StageTimer {
+    lfcuda_ctx* c; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(lfcuda_ctx* c_, int stage_) : c(c_), stage(stage_) {
+        c->launches++;
+        c->stats.launches[stage]++;
+        if (c->profiling) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    }
+    ~StageTimer() {
+        if (c->profiling) { cudaEventRecord(b, c->stream); c->events.push_back({stage, a, b}); }
+    }
+};
+
+int check_ready(lfcuda_ctx* ctx) {
+    if (!ctx) return LFCUDA_EINVAL;
+    if (!ctx->have_scene) return fail(ctx, LFCUDA_EINVAL, "no scene uploaded (lfcuda_upload_scene)");
+    if (!ctx->have_params) return fail(ctx, LFCUDA_EINVAL, "render parameters not set (lfcuda_set_params)");
+    if (!ctx->have_camera) return fail(ctx, LFCUDA_EINVAL, "camera not set (lfcuda_set_camera)");
+    return 0;
+}
+
+void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
+    L.scene = c->dev; L.params = D; L.soa = c->soa; L.queues = c->queues; L.counters = c->d_counters; L.stream = c->stream;
+    L.sm_count = c->prop.multiProcessorCount;
+    L.persistent_blocks = L.sm_count * 8;
+    L.stack_depth = c->packed.stack_depth;
+    L.cull = !c->params.no_cull;
+    L.count = c->params.count_work != 0;
+}
+
+// One batch of `nframes` (<= frames_cap) frames of one tile through the pipeline.
+int run_batch(lfcuda_ctx* ctx, int first_frame, int nframes, int stride, int tile_x, int tile_y, bool accumulate) {
+    DevParams D;
+    fill_dev_params(ctx, D, first_frame, nframes, stride, tile_x, tile_y);
+    LaunchCtx L;
+    make_launch_ctx(ctx, L, D);
+    if (ctx->params.kernel_mode == 1) {
+        { StageTimer t(ctx, LF_STAGE_MEGAKERNEL); launch_megakernel(L); }
+    } else {
+        CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)4 * ctx->queues.stride * sizeof(int), ctx->stream));
+        { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
+        for (int d = 0; d < D.max_depth; d++) {
+            { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, d); }
+            { StageTimer t(ctx, LF_STAGE_SHADE); launch_shade(L, d); }
+            { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
+        }
+    }
+    if (accumulate) { StageTimer t(ctx, LF_STAGE_ACCUMULATE); launch_accumulate(L, ctx->d_accum); }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+bool load_nccl(lfcuda_ctx* c) {
+    if (c->nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        c->nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (c->nccl.lib) break;
+    }
+    if (!c->nccl.lib) return false;
+    *(void**)&c->nccl.GetUniqueId = dlsym(c->nccl.lib, "ncclGetUniqueId");
+    *(void**)&c->nccl.CommInitRank = dlsym(c->nccl.lib, "ncclCommInitRank");
+    *(void**)&c->nccl.AllReduce = dlsym(c->nccl.lib, "ncclAllReduce");
+    *(void**)&c->nccl.CommDestroy = dlsym(c->nccl.lib, "ncclCommDestroy");
+    *(void**)&c->nccl.GetErrorString = dlsym(c->nccl.lib, "ncclGetErrorString");
+    return c->nccl.GetUniqueId && c->nccl.CommInitRank && c->nccl.AllReduce && c->nccl.CommDestroy;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lfcuda_abi_version(void) { return LFCUDA_ABI_VERSION; }
+
+int lfcuda_create(lfcuda_ctx** out, int device) {
+    lfcuda_ctx* ctx = nullptr;   // CK reports into g_create_error while ctx == nullptr
+    if (!out) return fail(nullptr, LFCUDA_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, LFCUDA_ECUDA, "no CUDA device available (%s); liblfcuda has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, LFCUDA_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    lfcuda_ctx* c = new lfcuda_ctx;
+    c->device = device;
+    ctx = c;
+    cudaError_t e2 = cudaGetDeviceProperties(&c->prop, device);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&c->d_counters, sizeof(DevCounters));
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->d_counters, 0, sizeof(DevCounters));
+    if (e2 != cudaSuccess) {
+        fail(nullptr, LFCUDA_ECUDA, "context setup failed: %s", cudaGetErrorString(e2));
+        delete c;
+        return LFCUDA_ECUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return 0;
+}
+
+void lfcuda_destroy(lfcuda_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+    for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    free_scene(c);
+    free_state(c);
+    cudaFree(c->d_counters);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* lfcuda_last_error(const lfcuda_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int lfcuda_set_stream(lfcuda_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return LFCUDA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int lfcuda_synchronize(lfcuda_ctx* ctx) {
+    if (!ctx) return LFCUDA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int lfcuda_upload_scene(lfcuda_ctx* ctx, const LfSceneView* v) {
+    if (!ctx || !v) return LFCUDA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    ctx->packed = PackedScene{};
+    std::string err;
+    if (!repack_scene(*v, ctx->packed, err)) return fail(ctx, LFCUDA_ELIMIT, "scene rejected: %s", err.c_str());
+    ctx->host_nodes.assign(v->bvh_nodes, v->bvh_nodes + (size_t)9 * v->num_nodes);
+    ctx->top_index = v->top_bvh_index;
+    ctx->num_tri_refs = v->num_tri_refs;
+    const PackedScene& P = ctx->packed;
+    DevScene& D = ctx->dev;
+    int r;
+    float4 *nodes, *tris, *trinrm, *inst, *mats, *lights; int* trivx;
+    // inner-node buffer sized for the worst case so that a TLAS rebuild (update_instances) never reallocates
+    ctx->nodes_cap = std::max<size_t>(P.nodes.size(), (size_t)4 * v->num_nodes);
+    CK(cudaMalloc((void**)&nodes, ctx->nodes_cap * sizeof(float4)));
+    ctx->scene_allocs.push_back(nodes);
+    CK(cudaMemcpyAsync(nodes, P.nodes.data(), P.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    if ((r = upload(ctx, P.tris.data(), P.tris.size(), &tris, ctx->scene_allocs))) return r;
+    if ((r = upload(ctx, P.trinrm.data(), P.trinrm.size(), &trinrm, ctx->scene_allocs))) return r;
+    if ((r = upload(ctx, P.tri_vx.data(), P.tri_vx.size(), &trivx, ctx->scene_allocs))) return r;
+    if ((r = upload(ctx, P.inst.data(), P.inst.size(), &inst, ctx->scene_allocs))) return r;
+    if ((r = upload(ctx, reinterpret_cast<const float4*>(v->materials), (size_t)7 * v->num_materials, &mats, ctx->scene_allocs))) return r;
+    if ((r = upload(ctx, P.lights.data(), P.lights.size(), &lights, ctx->scene_allocs))) return r;
+    ctx->d_nodes = nodes; ctx->d_inst = inst; ctx->d_materials = mats; ctx->materials_cap = v->num_materials;
+    D.nodes = nodes; D.tris = tris; D.trinrm = trinrm; D.tri_vx = trivx; D.inst = inst; D.materials = mats; D.lights = lights;
+    D.top_ref = P.top_ref;
+    D.num_lights = v->num_lights; D.num_materials = v->num_materials; D.num_instances = v->num_instances;
+
+    if (v->num_textures > 0 && v->texture_maps) {   // Renderer.cpp:151-160
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+        cudaExtent ext = make_cudaExtent(v->tex_width, v->tex_height, v->num_textures);
+        CK(cudaMalloc3DArray(&ctx->tex_array, &cd, ext, cudaArrayLayered));
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr((void*)v->texture_maps, (size_t)v->tex_width * 4, v->tex_width, v->tex_height);
+        cp.dstArray = ctx->tex_array;
+        cp.extent = ext;
+        cp.kind = cudaMemcpyHostToDevice;
+        CK(cudaMemcpy3D(&cp));
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = ctx->tex_array;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&D.tex_maps, &rd, &td, nullptr));
+        D.tex_w = v->tex_width; D.tex_h = v->tex_height; D.num_tex = v->num_textures;
+    }
+    if (v->hdr_cols && v->hdr_width > 0 && v->hdr_height > 0) {   // Renderer.cpp:163-185
+        size_t n = (size_t)v->hdr_width * v->hdr_height;
+        std::vector<float4> rgba(n);
+        for (size_t i = 0; i < n; i++) { rgba[i].x = v->hdr_cols[3 * i]; rgba[i].y = v->hdr_cols[3 * i + 1]; rgba[i].z = v->hdr_cols[3 * i + 2]; rgba[i].w = 1.f; }
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
+        CK(cudaMallocArray(&ctx->hdr_array, &cd, v->hdr_width, v->hdr_height));
+        CK(cudaMemcpy2DToArray(ctx->hdr_array, 0, 0, rgba.data(), (size_t)v->hdr_width * sizeof(float4), (size_t)v->hdr_width * sizeof(float4),
+                               v->hdr_height, cudaMemcpyHostToDevice));
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = ctx->hdr_array;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&D.hdr_tex, &rd, &td, nullptr));
+        float2 *marg, *cond;
+        if ((r = upload(ctx, reinterpret_cast<const float2*>(v->hdr_marginal), (size_t)v->hdr_height, &marg, ctx->scene_allocs))) return r;
+        if ((r = upload(ctx, reinterpret_cast<const float2*>(v->hdr_conditional), n, &cond, ctx->scene_allocs))) return r;
+        D.marginal = marg; D.conditional = cond;
+        D.hdr_w = v->hdr_width; D.hdr_h = v->hdr_height;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_scene = true;
+    return 0;
+}
+
+int lfcuda_update_instances(lfcuda_ctx* ctx, const float* transforms, int32_t num_instances, const float* materials, int32_t num_materials,
+                            const float* tlas_nodes, int32_t first_node, int32_t num_tlas_nodes) {
+    if (!ctx || !ctx->have_scene) return fail(ctx, LFCUDA_EINVAL, "no scene uploaded");
+    if (!transforms || num_instances != ctx->dev.num_instances) return fail(ctx, LFCUDA_EINVAL, "instance count changed (%d != %d)", num_instances, ctx->dev.num_instances);
+    int total = (int)(ctx->host_nodes.size() / 9);
+    if (!tlas_nodes || first_node < 0 || first_node + num_tlas_nodes > total) return fail(ctx, LFCUDA_EINVAL, "TLAS node range out of bounds");
+    if (materials && num_materials > ctx->materials_cap) return fail(ctx, LFCUDA_EINVAL, "material count grew (%d > %d)", num_materials, ctx->materials_cap);
+    CK(cudaSetDevice(ctx->device));
+    std::memcpy(ctx->host_nodes.data() + (size_t)9 * first_node, tlas_nodes, (size_t)9 * num_tlas_nodes * sizeof(float));
+    std::string err;
+    if (!repack_instances(ctx->host_nodes.data(), total, ctx->top_index, transforms, num_instances, ctx->packed, err))
+        return fail(ctx, LFCUDA_ELIMIT, "instance update rejected: %s", err.c_str());
+    if (ctx->packed.nodes.size() > ctx->nodes_cap) return fail(ctx, LFCUDA_ELIMIT, "inner node count grew past the uploaded capacity");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_nodes, ctx->packed.nodes.data(), ctx->packed.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_inst, ctx->packed.inst.data(), ctx->packed.inst.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    if (materials) {
+        CK(cudaMemcpyAsync(ctx->d_materials, materials, (size_t)28 * num_materials * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->dev.num_materials = num_materials;
+    }
+    ctx->dev.top_ref = ctx->packed.top_ref;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int lfcuda_set_params(lfcuda_ctx* ctx, const LfParams* p) {
+    if (!ctx || !p) return LFCUDA_EINVAL;
+    if (p->width <= 0 || p->height <= 0 || p->tile_width <= 0 || p->tile_height <= 0 || p->max_depth < 0)
+        return fail(ctx, LFCUDA_EINVAL, "bad resolution / tile size / depth");
+    CK(cudaSetDevice(ctx->device));
+    bool realloc = !ctx->have_params || p->width != ctx->params.width || p->height != ctx->params.height || p->tile_width != ctx->params.tile_width ||
+                   p->tile_height != ctx->params.tile_height || p->max_depth != ctx->params.max_depth || p->frames_in_flight != ctx->params.frames_in_flight;
+    ctx->params = *p;
+    ctx->have_params = true;
+    if (realloc) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        int r = alloc_state(ctx);
+        if (r) { ctx->have_params = false; return r; }
+    }
+    return 0;
+}
+
+int lfcuda_set_camera(lfcuda_ctx* ctx, const LfCamera* c) {
+    if (!ctx || !c) return LFCUDA_EINVAL;
+    ctx->camera = *c;
+    ctx->have_camera = true;
+    return 0;
+}
+
+int lfcuda_clear(lfcuda_ctx* ctx) {
+    if (!ctx || !ctx->have_params) return fail(ctx, LFCUDA_EINVAL, "render parameters not set");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_accum, 0, ctx->accum_floats * sizeof(float), ctx->stream));
+    return 0;
+}
+
+int lfcuda_render_frames(lfcuda_ctx* ctx, int32_t first_frame, int32_t nframes, int32_t frame_stride, int32_t tile_x, int32_t tile_y) {
+    int r = check_ready(ctx);
+    if (r) return r;
+    if (nframes < 0) return fail(ctx, LFCUDA_EINVAL, "nframes < 0");
+    CK(cudaSetDevice(ctx->device));
+    for (int done = 0; done < nframes;) {
+        int n = std::min(ctx->frames_cap, nframes - done);
+        r = run_batch(ctx, first_frame + done * frame_stride, n, frame_stride, tile_x, tile_y, true);
+        if (r) return r;
+        done += n;
+    }
+    return 0;
+}
+
+int lfcuda_read_accum(lfcuda_ctx* ctx, float* rgb_out) {
+    if (!ctx || !ctx->have_params || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "render parameters not set or NULL output");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(rgb_out, ctx->d_accum, ctx->accum_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int lfcuda_read_output(lfcuda_ctx* ctx, float inv_sample_counter, int32_t tonemap_index, float* rgb_out) {
+    if (!ctx || !ctx->have_params || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "render parameters not set or NULL output");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches++;
+    launch_post(ctx->stream, ctx->d_accum, ctx->d_out_f, nullptr, ctx->params.width * ctx->params.height, inv_sample_counter, tonemap_index);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb_out, ctx->d_out_f, ctx->accum_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int lfcuda_read_output_u8(lfcuda_ctx* ctx, float inv_sample_counter, int32_t tonemap_index, uint8_t* rgb_out) {
+    if (!ctx || !ctx->have_params || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "render parameters not set or NULL output");
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches++;
+    launch_post(ctx->stream, ctx->d_accum, nullptr, ctx->d_out_u8, ctx->params.width * ctx->params.height, inv_sample_counter, tonemap_index);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb_out, ctx->d_out_u8, ctx->accum_floats, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int lfcuda_accum_device_ptr(lfcuda_ctx* ctx, void** dev_ptr, size_t* num_floats) {
+    if (!ctx || !ctx->have_params) return fail(ctx, LFCUDA_EINVAL, "render parameters not set");
+    if (dev_ptr) *dev_ptr = ctx->d_accum;
+    if (num_floats) *num_floats = ctx->accum_floats;
+    return 0;
+}
+
+int lfcuda_read_primary_hits(lfcuda_ctx* ctx, int32_t frame, float* t_out, int32_t* tri_out, int32_t* mat_out, int32_t* emitter_out) {
+    int r = check_ready(ctx);
+    if (r) return r;
+    if (!t_out || !tri_out || !mat_out || !emitter_out) return fail(ctx, LFCUDA_EINVAL, "NULL output");
+    CK(cudaSetDevice(ctx->device));
+    // The probe covers the full frame as one tile, like the llvmpipe probe shader run on a single-tile scene.
+    LfParams saved = ctx->params;
+    LfParams full = saved;
+    full.tile_width = saved.width; full.tile_height = saved.height; full.kernel_mode = 0;
+    if ((r = lfcuda_set_params(ctx, &full))) return r;
+    size_t n = (size_t)saved.width * saved.height;
+    float* d_t; int *d_tri, *d_mat, *d_em;
+    CK(cudaMalloc((void**)&d_t, n * 4)); CK(cudaMalloc((void**)&d_tri, n * 4)); CK(cudaMalloc((void**)&d_mat, n * 4)); CK(cudaMalloc((void**)&d_em, n * 4));
+    DevParams D;
+    fill_dev_params(ctx, D, frame, 1, 1, 0, 0);
+    LaunchCtx L;
+    make_launch_ctx(ctx, L, D);
+    CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)4 * ctx->queues.stride * sizeof(int), ctx->stream));
+    { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
+    { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, 0); }
+    ctx->launches++;
+    launch_export_hits(L, d_t, d_tri, d_mat, d_em);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(t_out, d_t, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(tri_out, d_tri, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(mat_out, d_mat, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(emitter_out, d_em, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_t); cudaFree(d_tri); cudaFree(d_mat); cudaFree(d_em);
+    return lfcuda_set_params(ctx, &saved);
+}
+
+int lfcuda_nccl_unique_id(void* id128_out) {
+    if (!id128_out) return LFCUDA_EINVAL;
+    lfcuda_ctx tmp;
+    if (!load_nccl(&tmp)) return fail(nullptr, LFCUDA_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    int rc = tmp.nccl.GetUniqueId(id128_out);
+    return rc == 0 ? 0 : fail(nullptr, LFCUDA_ENCCL, "ncclGetUniqueId failed (%d)", rc);
+}
+
+int lfcuda_nccl_init(lfcuda_ctx* ctx, const void* id128, int32_t rank, int32_t nranks) {
+    if (!ctx || !id128) return LFCUDA_EINVAL;
+    if (!load_nccl(ctx)) return fail(ctx, LFCUDA_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    CK(cudaSetDevice(ctx->device));
+    NcclId id;
+    std::memcpy(&id, id128, 128);
+    int rc = ctx->nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (rc != 0) return fail(ctx, LFCUDA_ENCCL, "ncclCommInitRank failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(rc) : "?");
+    return 0;
+}
+
+int lfcuda_reduce(lfcuda_ctx* ctx) {
+    if (!ctx || !ctx->have_params) return fail(ctx, LFCUDA_EINVAL, "render parameters not set");
+    if (!ctx->comm) return fail(ctx, LFCUDA_ENCCL, "NCCL communicator not initialised (lfcuda_nccl_init)");
+    CK(cudaSetDevice(ctx->device));
+    // ncclFloat32 = 7, ncclSum = 0
+    int rc = ctx->nccl.AllReduce(ctx->d_accum, ctx->d_accum, ctx->accum_floats, 7, 0, ctx->comm, ctx->stream);
+    if (rc != 0) return fail(ctx, LFCUDA_ENCCL, "ncclAllReduce failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(rc) : "?");
+    return 0;
+}
+
+int lfcuda_reset_counters(lfcuda_ctx* ctx) {
+    if (!ctx) return LFCUDA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DevCounters), ctx->stream));
+    return 0;
+}
+
+int lfcuda_get_counters(lfcuda_ctx* ctx, LfCounters* out) {
+    if (!ctx || !out) return LFCUDA_EINVAL;
+    static_assert(sizeof(LfCounters) == sizeof(DevCounters), "counter layouts must match");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int lfcuda_set_profiling(lfcuda_ctx* ctx, int32_t on) {
+    if (!ctx) return LFCUDA_EINVAL;
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int lfcuda_get_stage_stats(lfcuda_ctx* ctx, LfStageStats* out) {
+    if (!ctx || !out) return LFCUDA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& ev : ctx->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) ctx->stats.ms[ev.stage] += ms;
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    }
+    ctx->events.clear();
+    *out = ctx->stats;
+    return 0;
+}
+
+int lfcuda_get_launch_count(lfcuda_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return LFCUDA_EINVAL;
+    *out = ctx->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// CudaRenderer.cpp — see CudaRenderer.h.  The state machine restates TiledRenderer::Init/Update/Render
+// (LavaFrame/TiledRenderer.cpp:48-64, 317-352, 421-521); GPU work is deferred and batched: Render() only
+// queues its (frame, tile) step, and queued steps of COMPLETED samples are launched together (consecutive
+// frames of one tile become a single lfcuda_render_frames call), which is unobservable through the interface
+// because the reference also exposes only the image of the last completed sample (tileOutputTexture[1 - currentBuffer]).
+#include "CudaRenderer.h"
+
+#include <cmath>
+#include <cstdio>
+
+#include "Camera.h"
+#include "Scene.h"
+#include "scene_view.h"
+
+namespace LavaFrame
+{
+    CudaRenderer::CudaRenderer(Scene* scene, const std::string& shadersDirectory, int device_)
+        : Renderer(scene, shadersDirectory)
+        , ctx(nullptr), device(device_)
+        , tileX(-1), tileY(-1), numTilesX(-1), numTilesY(-1)
+        , tileWidth(scene->renderOptions.tileWidth), tileHeight(scene->renderOptions.tileHeight)
+        , currentBuffer(0), frameCounter(1), sampleCounter(0)
+    {
+    }
+
+    CudaRenderer::~CudaRenderer()
+    {
+        if (initialized) this->Finish();
+    }
+
+    const char* CudaRenderer::LastError() const { return ctx ? lfcuda_last_error(ctx) : error.c_str(); }
+
+    void CudaRenderer::Init()
+    {
+        if (initialized) return;
+        Renderer::Init();
+        if (!initialized) return;
+        initialized = false;
+
+        sampleCounter = 1;                                   // TiledRenderer.cpp:55-64
+        currentBuffer = 0;
+        frameCounter = 1;
+        numTilesX = (int)ceil((float)screenSize.x / tileWidth);
+        numTilesY = (int)ceil((float)screenSize.y / tileHeight);
+        tileX = -1;
+        tileY = numTilesY - 1;
+
+        if (lfcuda_create(&ctx, device) != 0) {
+            error = lfcuda_last_error(nullptr);
+            printf("CudaRenderer: %s\n", error.c_str());    // like the reference: print and return (Renderer.cpp:81-85)
+            return;
+        }
+        LfSceneView view;
+        lfhost::MakeSceneView(scene, &view);
+        if (lfcuda_upload_scene(ctx, &view) != 0) { printf("CudaRenderer: %s\n", lfcuda_last_error(ctx)); return; }
+        UploadUniforms();
+        if (lfcuda_clear(ctx) != 0) { printf("CudaRenderer: %s\n", lfcuda_last_error(ctx)); return; }
+        initialized = true;
+    }
+
+    void CudaRenderer::UploadUniforms()
+    {
+        LfParams params;
+        LfCamera cam;
+        lfhost::MakeParams(scene, &params);
+        lfhost::MakeCamera(scene, &cam);
+        if (lfcuda_set_params(ctx, &params) != 0 || lfcuda_set_camera(ctx, &cam) != 0)
+            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+    }
+
+    void CudaRenderer::Finish()
+    {
+        if (!initialized) return;
+        pending.clear();
+        lfcuda_destroy(ctx);
+        ctx = nullptr;
+        Renderer::Finish();
+    }
+
+    void CudaRenderer::Execute(size_t count)
+    {
+        // consecutive frames of the same tile -> one batched call
+        size_t i = 0;
+        while (i < count) {
+            size_t j = i + 1;
+            while (j < count && pending[j].tileX == pending[i].tileX && pending[j].tileY == pending[i].tileY &&
+                   pending[j].frame == pending[j - 1].frame + 1) j++;
+            if (lfcuda_render_frames(ctx, pending[i].frame, (int)(j - i), 1, pending[i].tileX, pending[i].tileY) != 0)
+                printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+            i = j;
+        }
+        pending.erase(pending.begin(), pending.begin() + count);
+    }
+
+    void CudaRenderer::FlushCompletedSamples()
+    {
+        size_t n = 0;
+        while (n < pending.size() && pending[n].sample < sampleCounter) n++;
+        if (n) Execute(n);
+    }
+
+    void CudaRenderer::Flush() { if (!pending.empty()) Execute(pending.size()); }
+
+    void CudaRenderer::Render()
+    {
+        if (!initialized) { printf("Renderer is not initialized.\n"); return; }   // TiledRenderer.cpp:319-323
+        if (scene->camera->isMoving || scene->instancesModified) {
+            scene->instancesModified = false;    // the reference draws its low-res preview here (:325-333); no preview when headless
+            return;
+        }
+        pending.push_back(Step{frameCounter, tileX, tileY, sampleCounter});
+        if (pending.size() >= 4096) FlushCompletedSamples();
+    }
+
+    float CudaRenderer::GetProgress() const
+    {
+        return float((numTilesY - tileY - 1) * numTilesX + tileX) / float(numTilesX * numTilesY);   // TiledRenderer.cpp:377-380
+    }
+
+    int CudaRenderer::GetSampleCount() const { return sampleCounter; }
+
+    void CudaRenderer::Update(float secondsElapsed)
+    {
+        if (!initialized) return;
+        if (scene->instancesModified) {          // Renderer::Update, Renderer.cpp:190-205
+            int index = scene->bvhTranslator.topLevelIndex;
+            int total = (int)scene->bvhTranslator.nodes.size();
+            if (lfcuda_update_instances(ctx, reinterpret_cast<const float*>(scene->transforms.data()), (int)scene->transforms.size(),
+                                        reinterpret_cast<const float*>(scene->materials.data()), (int)scene->materials.size(),
+                                        reinterpret_cast<const float*>(&scene->bvhTranslator.nodes[index]), index, total - index) != 0)
+                printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+        }
+        if (scene->camera->isMoving || scene->instancesModified) {   // TiledRenderer.cpp:471-484
+            tileX = -1;
+            tileY = numTilesY - 1;
+            sampleCounter = 1;
+            frameCounter = 1;
+            pending.clear();
+            lfcuda_clear(ctx);
+        } else {                                                     // :485-501
+            frameCounter++;
+            tileX++;
+            if (tileX >= numTilesX) {
+                tileX = 0;
+                tileY--;
+                if (tileY < 0) {
+                    tileX = 0;
+                    tileY = numTilesY - 1;
+                    sampleCounter++;
+                    currentBuffer = 1 - currentBuffer;
+                }
+            }
+        }
+        UploadUniforms();                                            // :505-521 (camera, maxDepth, hdrMultiplier, bgColor ...)
+    }
+
+    void CudaRenderer::GetOutputBufferHDR(float** data, int& w, int& h)
+    {
+        w = scene->renderOptions.resolution.x;                       // TiledRenderer.cpp:399-414
+        h = scene->renderOptions.resolution.y;
+        *data = new float[(size_t)w * h * 3];
+        if (!initialized) return;
+        FlushCompletedSamples();
+        int completed = sampleCounter - 1;                           // what tileOutputTexture[1 - currentBuffer] holds
+        float inv = 1.0f / (float)(completed > 0 ? completed : 1);   // invSampleCounter, TiledRenderer.cpp:542
+        if (lfcuda_read_output(ctx, inv, scene->renderOptions.tonemapIndex, *data) != 0)
+            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+    }
+
+    void CudaRenderer::GetOutputBuffer(unsigned char** data, int& w, int& h)
+    {
+        w = scene->renderOptions.resolution.x;                       // TiledRenderer.cpp:382-397
+        h = scene->renderOptions.resolution.y;
+        *data = new unsigned char[(size_t)w * h * 3];
+        if (!initialized) return;
+        FlushCompletedSamples();
+        int completed = sampleCounter - 1;
+        float inv = 1.0f / (float)(completed > 0 ? completed : 1);
+        if (lfcuda_read_output_u8(ctx, inv, scene->renderOptions.tonemapIndex, *data) != 0)
+            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+    }
+}

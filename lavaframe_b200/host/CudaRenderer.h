@@ -1,0 +1,61 @@
+// CudaRenderer.h — drop-in replacement for LavaFrame::TiledRenderer behind the reference's own Renderer
+// interface (LavaFrame/Renderer.h:71-117).  Construct it where the reference constructs its renderer:
+//
+//     GlobalState.renderer = new CudaRenderer(GlobalState.scene, GlobalState.shadersDir);   // Main.cpp:91
+//
+// Same call protocol (Init once; every loop iteration Update(dt) then Render(); GetSampleCount() ==
+// completed samples + 1; GetOutputBuffer[HDR] returns the image of the last COMPLETED sample, bottom row
+// first, allocated with new[]), same tile / frame / sample counters as TiledRenderer.cpp:55-64,485-501, so the
+// `frame` uniform that seeds the RNG takes the same values.  All rendering goes through the C ABI of
+// include/lfcuda.h; there is no OpenGL and no CPU fallback.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "Renderer.h"
+#include "lfcuda.h"
+
+namespace LavaFrame
+{
+    class Scene;
+
+    class CudaRenderer : public Renderer
+    {
+    public:
+        CudaRenderer(Scene* scene, const std::string& shadersDirectory, int device = 0);
+        ~CudaRenderer();
+
+        void Init() override;
+        void Finish() override;
+        void Render() override;
+        void Present() const override {}                         // no window in the headless build
+        void Update(float secondsElapsed) override;
+        float GetProgress() const override;
+        int GetSampleCount() const override;
+        void GetOutputBuffer(unsigned char**, int& w, int& h) override;
+        void GetOutputBufferHDR(float** data, int& w, int& h) override;
+        uint32_t SetViewport(int, int) override { return 0; }    // returned a GL texture id
+        uint32_t Denoise() override { return 0; }                // OIDN is not part of the path
+
+        // Extras for drivers/tests (not part of the reference interface)
+        lfcuda_ctx* Context() const { return ctx; }
+        const char* LastError() const;
+        void Flush();                                            // execute every queued tile step now
+
+    private:
+        struct Step { int frame, tileX, tileY, sample; };
+        void FlushCompletedSamples();
+        void Execute(size_t count);
+        void UploadUniforms();
+
+        lfcuda_ctx* ctx;
+        int device;
+        std::vector<Step> pending;       // tile steps requested by Render() and not yet launched
+
+        int tileX, tileY, numTilesX, numTilesY, tileWidth, tileHeight;
+        int currentBuffer, frameCounter, sampleCounter;
+        std::string error;
+    };
+}

@@ -1,0 +1,68 @@
+// lf_render — headless driver: what LavaFrame/Main.cpp does with `-s scene -ms N -u -w`, minus SDL/ImGui/GL:
+// load the scene with the reference's loader, construct the renderer, loop Update -> Render until
+// `maxSamples + 1 == GetSampleCount()` (Main.cpp:197), then fetch GetOutputBufferHDR.
+//
+//   lf_render <scene> --spp N [--out img.f32] [--device D] [--tonemap] [--megakernel]
+// img.f32: W*H*3 float32, rows bottom-up (the exporters flip, Export.h:19).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "Scene.h"
+#include "Loader.h"
+#include "GlobalState.h"
+#include "../CudaRenderer.h"
+
+using namespace LavaFrame;
+extern LavaFrameState GlobalState;
+
+int main(int argc, char** argv) {
+    if (argc < 2) { fprintf(stderr, "usage: lf_render <scene> --spp N [--out img.f32] [--device D] [--tonemap]\n"); return 2; }
+    std::string out;
+    int spp = 1, device = 0;
+    bool keepTonemap = false;
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--spp") spp = atoi(argv[++i]);
+        else if (a == "--out") out = argv[++i];
+        else if (a == "--device") device = atoi(argv[++i]);
+        else if (a == "--tonemap") keepTonemap = true;
+        else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    RenderOptions ro;
+    ro.useVignette = false; ro.vignetteIntensity = 0.f; ro.vignettePower = 1.f;
+    if (!keepTonemap) ro.tonemapIndex = 0;
+    GlobalState.scene = new Scene();
+    if (!LoadSceneFromFile(argv[1], GlobalState.scene, ro)) return 1;
+    if (!keepTonemap) ro.tonemapIndex = 0;
+    GlobalState.scene->renderOptions = ro;
+    GlobalState.scene->camera->isMoving = false;
+
+    CudaRenderer* r = new CudaRenderer(GlobalState.scene, GlobalState.shadersDir, device);   // Main.cpp:91
+    GlobalState.renderer = r;
+    r->Init();
+    if (!r->Context()) { fprintf(stderr, "lf_render: %s\n", r->LastError()); return 3; }
+    auto t0 = std::chrono::steady_clock::now();
+    int steps = 0;
+    while (true) {
+        if (r->GetSampleCount() == spp + 1) break;
+        r->Update(0.f);
+        if (r->GetSampleCount() == spp + 1) break;
+        r->Render();
+        steps++;
+    }
+    float* img = nullptr;
+    int w = 0, h = 0;
+    r->GetOutputBufferHDR(&img, w, h);
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    double sum[3] = {0, 0, 0};
+    for (long i = 0; i < (long)w * h; i++) for (int k = 0; k < 3; k++) sum[k] += img[3 * i + k];
+    printf("{\"impl\": \"cuda\", \"width\": %d, \"height\": %d, \"spp\": %d, \"tile_steps\": %d, \"seconds\": %.4f, \"samples_per_s\": %.1f, "
+           "\"mean_rgb\": [%.8g, %.8g, %.8g]}\n", w, h, spp, steps, sec, (double)w * h * spp / sec, sum[0] / (w * h), sum[1] / (w * h), sum[2] / (w * h));
+    if (!out.empty()) { FILE* f = fopen(out.c_str(), "wb"); fwrite(img, 4, (size_t)w * h * 3, f); fclose(f); }
+    delete[] img;
+    delete r;
+    return 0;
+}

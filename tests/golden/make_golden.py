@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures of tests/golden/ from THE REFERENCE ITSELF.
+
+Runs only in the authoring container (needs /root/reference, built into oracle/_ref by `make -C oracle ref`
+and lavaframe_b200/bin/lf_scenepack by CMake):
+
+  * <name>.lfpack            the flattened scene arrays, produced by the reference's unchanged loader + BVH builder
+  * <name>_llvmpipe.npz      outputs of the reference's unmodified TiledRenderer + GLSL on Mesa llvmpipe:
+        hits_t / hits_tri / hits_mat / hits_emitter   first camera ray of frame 2 ("--probe hits")
+        spp1                                           1-spp radiance (frame 2), W*H*3 float32, rows bottom-up
+        sppN                                           N-spp mean (frames 2..N+1)
+
+Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] ...
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from scenes import gen_scenes  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "lf_ref_llvmpipe")
+PACKBIN = os.path.join(ROOT, "lavaframe_b200", "bin", "lf_scenepack")
+
+# name -> (scene builder, N for the N-spp mean)
+SCENES = {
+    "cornell": (gen_scenes.cornell_256, 64),
+    "c2mini": (gen_scenes.c2_mini, 16),
+    "c3mini": (gen_scenes.c3_mini, 16),
+}
+
+
+def run_ref(scene, spp, out, probe=None):
+    cmd = [REFBIN, "--scene", scene, "--spp", str(spp), "--out", out, "--timing-json"]
+    if probe:
+        cmd += ["--probe", probe]
+    res = subprocess.run(cmd, env=gen_scenes.llvmpipe_env(), check=True, capture_output=True, text=True)
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def main(names):
+    for name in names:
+        builder, nspp = SCENES[name]
+        with tempfile.TemporaryDirectory() as tmp:
+            scene = builder(os.path.join(tmp, "assets"))
+            pack = os.path.join(GOLD, f"{name}.lfpack")
+            subprocess.run([PACKBIN, scene, pack], check=True)
+            info = run_ref(scene, 1, os.path.join(tmp, "hits.f32"), probe="hits")
+            W, H = info["width"], info["height"]
+            hits = np.fromfile(os.path.join(tmp, "hits.f32"), np.float32).reshape(H, W, 3)
+            run_ref(scene, 1, os.path.join(tmp, "s1.f32"))
+            s1 = np.fromfile(os.path.join(tmp, "s1.f32"), np.float32).reshape(H, W, 3)
+            tN = run_ref(scene, nspp, os.path.join(tmp, "sN.f32"))
+            sN = np.fromfile(os.path.join(tmp, "sN.f32"), np.float32).reshape(H, W, 3)
+            assert W & (W - 1) == 0 and H & (H - 1) == 0, "golden scenes must have power-of-two sizes (exact LINEAR reads)"
+            tri_f = hits[..., 1]
+            emitter = (np.abs(tri_f - np.floor(tri_f)) == 0.5)
+            assert np.all(emitter | (tri_f == np.floor(tri_f)))
+            tri = np.where(emitter, -1, np.floor(tri_f)).astype(np.int32)
+            np.savez_compressed(os.path.join(GOLD, f"{name}_llvmpipe.npz"),
+                                hits_t=hits[..., 0], hits_tri=tri, hits_mat=hits[..., 2].astype(np.int32),
+                                hits_emitter=emitter.astype(np.int8), spp1=s1, sppN=sN, nspp=np.int32(nspp),
+                                gl_renderer=np.bytes_(tN["gl_renderer"]), gl_version=np.bytes_(tN["gl_version"]))
+            print(name, "->", pack, f"{W}x{H}", "mean", s1.mean(axis=(0, 1)), "steady samples/s", tN["samples_per_s_steady"])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["cornell"])

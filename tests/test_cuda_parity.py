@@ -1,0 +1,212 @@
+"""GPU tests (-m gpu): the CUDA path through the C ABI against the CPU oracle, the llvmpipe goldens, and
+size-independent properties.  Every call goes through liblfcuda.so's extern "C" entry points."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_api import Oracle
+from parity_metrics import hits_agreement, radiance_agreement, rmse_over_mean_luminance
+import lavaframe_b200 as lf
+
+pytestmark = pytest.mark.gpu
+
+SCENES = ["cornell", "c2mini", "c3mini"]
+
+
+def pack_path(golden_dir, name):
+    return os.path.join(golden_dir, f"{name}.lfpack")
+
+
+@pytest.fixture(scope="module")
+def tracer(gpu):
+    pt = lf.PathTracer(gpu)
+    yield pt
+    pt.close()
+
+
+def masked(tri, mat, em):
+    return np.where(em > 0, -1, tri), np.where(em > 0, -1, mat)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_primary_hits_vs_oracle(tracer, golden_dir, oracle_lib, name):
+    """Check 1 of the north_star, CUDA vs oracle: the arithmetic of a camera ray + traversal uses only + - * / sqrt,
+    so it must be identical bit for bit."""
+    pack = lf.ScenePack(pack_path(golden_dir, name))
+    tracer.upload_pack(pack)
+    t, tri, mat, em = tracer.primary_hits(2)
+    o = Oracle(pack.path)
+    ot, otri, omat, oem = o.primary_hits(2)
+    o.close()
+    assert np.array_equal(em > 0, oem > 0)
+    tri, mat = masked(tri, mat, em)
+    otri, omat = masked(otri, omat, oem)
+    same, both = hits_agreement(t, tri, mat, ot, otri, omat)
+    assert same == 1.0 and both == 1.0, f"{name}: ids {same:.6f}, ids+t {both:.6f}"
+    assert np.array_equal(t, ot), f"{name}: t differs in {(t != ot).sum()} pixels, max rel {np.max(np.abs(t - ot) / ot):.3e}"
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_primary_hits_vs_llvmpipe(tracer, golden_dir, name):
+    """Check 1 against the reference itself (golden from the unmodified GLSL on llvmpipe)."""
+    g = np.load(os.path.join(golden_dir, f"{name}_llvmpipe.npz"))
+    tracer.upload_pack(lf.ScenePack(pack_path(golden_dir, name)))
+    t, tri, mat, em = tracer.primary_hits(2)
+    tri, mat = masked(tri, mat, em)
+    gtri, gmat = masked(g["hits_tri"], g["hits_mat"], g["hits_emitter"])
+    same, both = hits_agreement(t, tri, mat, g["hits_t"], gtri, gmat)
+    assert same >= 0.9999 and both >= 0.9999, f"{name}: ids {same:.6f}, ids+t(1e-5) {both:.6f}"
+
+
+@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_radiance_vs_oracle(tracer, golden_dir, oracle_lib, name, mode):
+    """Check 2, CUDA vs oracle, wavefront (mode 0) and megakernel (mode 1): 1-spp radiance of frame 2 and a 4-frame sum."""
+    pack = lf.ScenePack(pack_path(golden_dir, name))
+    tracer.upload_pack(pack, kernel_mode=mode)
+    o = Oracle(pack.path)
+    for first, n in ((2, 1), (3, 4)):
+        tracer.clear()
+        tracer.render_frames(first, n)
+        img = tracer.read_accum()
+        ref = o.render_frames(first, n)
+        frac = radiance_agreement(img, ref)
+        exact = float(np.mean(np.all(img == ref, axis=2)))
+        assert frac >= MIN_VS_ORACLE[name], f"{name} mode {mode} frames {first}+{n}: within 1e-3 on {frac:.6f} (bit-exact on {exact:.6f})"
+    o.close()
+
+
+# CUDA vs oracle: same operation order, no FMA; the only differences are last-ulp results of sinf/cosf/powf/expf/logf/
+# acosf/atan2f between CUDA's and glibc's libm, which glass/metal chains amplify (see tests/test_oracle_golden.py).
+MIN_VS_ORACLE = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.98}
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_radiance_vs_llvmpipe(tracer, golden_dir, name):
+    """Checks 2 and 3 against the reference itself."""
+    g = np.load(os.path.join(golden_dir, f"{name}_llvmpipe.npz"))
+    tracer.upload_pack(lf.ScenePack(pack_path(golden_dir, name)))
+    tracer.clear()
+    tracer.render_frames(2, 1)
+    frac = radiance_agreement(tracer.read_accum(), g["spp1"])
+    assert frac >= MIN_VS_ORACLE[name], f"{name}: 1-spp within 1e-3 on {frac:.6f}"
+    n = int(g["nspp"])
+    tracer.clear()
+    tracer.render_frames(2, n)
+    mean = tracer.read_output(1.0 / n, 0)
+    assert rmse_over_mean_luminance(mean, g["sppN"]) < 0.05
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_wavefront_equals_megakernel(tracer, golden_dir, name):
+    """Two kernel organisations of the same device functions must agree bit for bit."""
+    pack = lf.ScenePack(pack_path(golden_dir, name))
+    imgs = []
+    for mode in (0, 1):
+        tracer.upload_pack(pack, kernel_mode=mode)
+        tracer.clear()
+        tracer.render_frames(2, 3)
+        imgs.append(tracer.read_accum())
+    assert np.array_equal(imgs[0], imgs[1]), f"{(imgs[0] != imgs[1]).any(axis=2).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_cull_does_not_change_results(tracer, golden_dir, name):
+    """The distance cull is the one deliberate departure from the reference's traversal; it must be invisible."""
+    pack = lf.ScenePack(pack_path(golden_dir, name))
+    res = []
+    for no_cull in (0, 1):
+        tracer.upload_pack(pack, no_cull=no_cull)
+        hits = tracer.primary_hits(2)
+        tracer.clear()
+        tracer.render_frames(2, 2)
+        res.append((hits, tracer.read_accum()))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_counters_match_oracle_without_cull(tracer, golden_dir, oracle_lib):
+    """With the cull off the kernel walks the BVH exactly like the reference: every closest-hit ray makes the same
+    visits.  Shadow rays whose NEE contribution is rejected whatever the visibility (bsdf pdf <= 0, MIS weight 0) are
+    not traced by the kernel (the reference traces, then discards them), so the shadow-side counts are upper-bounded."""
+    pack = lf.ScenePack(pack_path(golden_dir, "cornell"))
+    tracer.upload_pack(pack, no_cull=1, count_work=1)
+    tracer.reset_counters()
+    tracer.clear()
+    tracer.render_frames(2, 1)
+    c = tracer.counters()
+    o = Oracle(pack.path, cull=False, count=True)
+    o.render_frames(2, 1)
+    oc = o.counters()
+    o.close()
+    for k in ("samples", "rays_closest", "shaded_hits"):
+        assert c[k] == oc[k], (k, c[k], oc[k])
+    for k in ("rays_shadow", "inner_visits", "leaf_visits", "tlas_visits", "tri_tests", "light_tests"):
+        assert 0.5 * oc[k] <= c[k] <= oc[k], (k, c[k], oc[k])
+    # closest-hit-only comparison: a depth-1 render traces no rays the reference would not
+    tracer.update_params(max_depth=1)
+    tracer.reset_counters(); tracer.clear(); tracer.render_frames(2, 1)
+    c1 = tracer.counters()
+    o = Oracle(pack.path, cull=False, count=True)
+    o.update_params(max_depth=1)
+    o.render_frames(2, 1)
+    o1 = o.counters()
+    o.close()
+    assert c1["rays_closest"] == o1["rays_closest"] == 65536
+    closest_only = {k: c1[k] for k in ("inner_visits", "leaf_visits", "tlas_visits", "tri_tests")}
+    assert all(closest_only[k] <= o1[k] for k in closest_only)
+    tracer.update_params(count_work=0)
+
+
+def test_linearity_and_determinism(tracer, golden_dir):
+    """Accumulation is a plain per-pixel sum in frame order: rendering frames 2..9 in one call, in two calls, or
+    twice, gives identical bits; frame-strided subsets partition the sum (the multi-GPU split)."""
+    pack = lf.ScenePack(pack_path(golden_dir, "cornell"))
+    tracer.upload_pack(pack)
+    tracer.clear(); tracer.render_frames(2, 8); a = tracer.read_accum()
+    tracer.clear(); tracer.render_frames(2, 3); tracer.render_frames(5, 5); b = tracer.read_accum()
+    tracer.clear(); tracer.render_frames(2, 8); c = tracer.read_accum()
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    tracer.clear(); tracer.render_frames(2, 4, 2); even = tracer.read_accum()
+    tracer.clear(); tracer.render_frames(3, 4, 2); odd = tracer.read_accum()
+    np.testing.assert_allclose(even + odd, a, rtol=2e-6, atol=1e-7)
+
+
+def test_tiles_equal_full_frame(tracer, golden_dir):
+    """A dividing tile size renders the same pixel-samples: tile steps with the frame numbers TiledRenderer would
+    use for them reproduce per-tile what a single-tile run of those frames gives."""
+    pack = lf.ScenePack(pack_path(golden_dir, "cornell"))
+    tracer.upload_pack(pack)
+    tracer.clear(); tracer.render_frames(7, 1); full = tracer.read_accum()
+    tracer.upload_pack(pack, tile_width=128, tile_height=64)
+    tracer.clear()
+    for ty in range(4):
+        for tx in range(2):
+            tracer.render_frames(7, 1, 1, tx, ty)
+    tiled = tracer.read_accum()
+    frac = radiance_agreement(tiled, full, rel=1e-4)
+    assert frac >= 0.999, frac
+
+
+def test_postprocess_and_u8(tracer, golden_dir):
+    pack = lf.ScenePack(pack_path(golden_dir, "cornell"))
+    tracer.upload_pack(pack)
+    tracer.clear(); tracer.render_frames(2, 4)
+    acc = tracer.read_accum()
+    lin = tracer.read_output(0.25, 0)
+    np.testing.assert_array_equal(lin, acc * np.float32(0.25))
+    u8 = tracer.read_output_u8(0.25, 0)
+    np.testing.assert_array_equal(u8, np.rint(np.clip(lin, 0, 1) * 255).astype(np.uint8))
+    aces = tracer.read_output(0.25, 2)
+    c = lin.astype(np.float64)
+    ref = np.clip((c * (2.51 * c + 0.03)) / (c * (2.43 * c + 0.59) + 0.14), 0, 1) ** (1 / 2.2)
+    np.testing.assert_allclose(aces, ref, rtol=2e-5, atol=2e-6)
+
+
+def test_errors_are_reported(gpu):
+    pt = lf.PathTracer(gpu)
+    with pytest.raises(lf.LfCudaError, match="no scene"):
+        pt.render_frames(2, 1)
+    pt.close()
