@@ -122,6 +122,8 @@ typedef struct LfCounters {
     uint64_t env_nee;        /* EnvSample calls */
     uint64_t env_miss;       /* env lookups on miss */
     uint64_t tex_samples;    /* bilinear RGBA8 material-texture samples */
+    /* the share of the traversal counts above that belongs to AnyHit (shadow) rays */
+    uint64_t inner_visits_shadow, leaf_visits_shadow, tri_tests_shadow, tlas_visits_shadow, light_tests_shadow;
 } LfCounters;
 
 /* Device time per wavefront stage, measured with CUDA events on the context's stream while
@@ -200,6 +202,10 @@ int  lfcuda_set_profiling(lfcuda_ctx* ctx, int32_t on);
 int  lfcuda_get_stage_stats(lfcuda_ctx* ctx, LfStageStats* out);   /* synchronises */
 /* Number of CUDA kernels launched by this context since creation. */
 int  lfcuda_get_launch_count(lfcuda_ctx* ctx, uint64_t* out);
+/* Read-bandwidth probe for the roofline denominators MEASURED_PEAKS.json lacks (L2): `iters` passes of 16-byte
+ * read-only loads over a `bytes`-sized buffer by a full grid; GB/s of the best pass.  A working set well below the
+ * L2 size measures L2 -> SM bandwidth, one far above it measures HBM reads. */
+int  lfcuda_measure_read_bandwidth(lfcuda_ctx* ctx, size_t bytes, int32_t iters, double* gbps_out);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,9 @@ class LfCamera(C.Structure):
 
 class LfCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "rays_closest", "rays_shadow", "inner_visits", "leaf_visits", "tri_tests",
-                                          "tlas_visits", "light_tests", "shaded_hits", "env_nee", "env_miss", "tex_samples")]
+                                          "tlas_visits", "light_tests", "shaded_hits", "env_nee", "env_miss", "tex_samples",
+                                          "inner_visits_shadow", "leaf_visits_shadow", "tri_tests_shadow", "tlas_visits_shadow",
+                                          "light_tests_shadow")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -90,6 +92,7 @@ LFCUDA_SYMBOLS = {
     "lfcuda_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "lfcuda_get_stage_stats": (C.c_int, [C.c_void_p, C.POINTER(LfStageStats)]),
     "lfcuda_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "lfcuda_measure_read_bandwidth": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lfcuda = None

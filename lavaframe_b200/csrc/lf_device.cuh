@@ -164,7 +164,7 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
     // Analytic lights first (closest_hit.glsl:13-67, anyhit.glsl:11-46)
     for (int i = 0; i < S.num_lights; i++) {
         LightRec L = load_light(S, i);
-        bump<COUNT>(cnt, C_LIGHT);
+        bump<COUNT>(cnt, C_LIGHT); if (ANY) bump<COUNT>(cnt, C_LIGHT_SH);
         if (L.type == 0.f) {
             if (!ANY && dot(L.normal, r.d) > 0.f) continue;        // back-facing quad hidden from closest-hit only
             float d = RectIntersect(L.position, L.uu, L.vv, L.normal, L.planeW, r);
@@ -206,7 +206,7 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
             continue;
         }
         if (ref >= 0) {                           // inner node (closest_hit.glsl:167-199)
-            bump<COUNT>(cnt, C_INNER);
+            bump<COUNT>(cnt, C_INNER); if (ANY) bump<COUNT>(cnt, C_INNER_SH);
             const float4* n = S.nodes + (size_t)4 * ref;
             float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3);
             float le, re;
@@ -229,7 +229,7 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
             if (lok) { ref = leftRef; continue; }
             if (rok) { ref = rightRef; continue; }
         } else if (ref & kRefTlasBit) {           // TLAS leaf (closest_hit.glsl:148-166)
-            bump<COUNT>(cnt, C_TLAS);
+            bump<COUNT>(cnt, C_TLAS); if (ANY) bump<COUNT>(cnt, C_TLAS_SH);
             curInst = ref_instance(ref);
             const float4* ip = S.inst + (size_t)kInstStride * curInst;
             float4 r0 = ldg4(ip), r1 = ldg4(ip + 1), r2 = ldg4(ip + 2), meta = ldg4(ip + 3);
@@ -247,12 +247,12 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
             ref = __float_as_int(meta.x);
             continue;
         } else {                                  // BLAS leaf (closest_hit.glsl:108-147, anyhit.glsl:87-116)
-            bump<COUNT>(cnt, C_LEAF);
+            bump<COUNT>(cnt, C_LEAF); if (ANY) bump<COUNT>(cnt, C_LEAF_SH);
             int first = ref_leaf_first(ref), count = ref_leaf_count(ref);
             for (int i = 0; i < count; i++) {
                 const float4* tp = S.tris + (size_t)3 * (first + i);
                 float4 q0 = ldg4(tp), q1 = ldg4(tp + 1), q2 = ldg4(tp + 2);
-                bump<COUNT>(cnt, C_TRI);
+                bump<COUNT>(cnt, C_TRI); if (ANY) bump<COUNT>(cnt, C_TRI_SH);
                 f3 e0 = mk3(q1.x, q1.y, q1.z), e1 = mk3(q2.x, q2.y, q2.z);
                 f3 pv = cross(d, e1);
                 float det = dot(e0, pv);

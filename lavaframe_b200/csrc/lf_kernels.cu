@@ -407,6 +407,26 @@ __global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned c
     }
 }
 
+// ---------------------------------------------------------------------------------------------- bandwidth probe
+// 16-byte read-only loads (LDG.E.128.CONSTANT, the load the traversal uses) over a buffer, 4 independent loads in
+// flight per thread; the xor-sum keeps the loads alive.
+__global__ void __launch_bounds__(256) k_read_probe(const float4* __restrict__ buf, size_t n4, int passes, float* sink) {
+    float acc = 0.f;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int p = 0; p < passes; p++) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            float4 a = __ldg(buf + i), b = __ldg(buf + i + stride), c = __ldg(buf + i + 2 * stride), d = __ldg(buf + i + 3 * stride);
+            acc += (a.x + b.y) + (c.z + d.w);
+        }
+        for (; i < n4; i += stride) acc += __ldg(buf + i).x;
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int passes, float* sink, int blocks) {
+    k_read_probe<<<blocks, 256, 0, stream>>>(buf, n4, passes, sink);
+}
+
 // ---------------------------------------------------------------------------------------------- launchers
 template <bool CULL, bool COUNT, int STACK>
 static void launch_trace_kernels_t(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {

@@ -104,8 +104,9 @@ struct Queues {
 };
 
 struct DevCounters {   // mirrors LfCounters, device side
-    unsigned long long v[12];
+    unsigned long long v[17];
 };
-enum { C_SAMPLES = 0, C_RAYS_CLOSEST, C_RAYS_SHADOW, C_INNER, C_LEAF, C_TRI, C_TLAS, C_LIGHT, C_SHADED, C_ENV_NEE, C_ENV_MISS, C_TEX };
+enum { C_SAMPLES = 0, C_RAYS_CLOSEST, C_RAYS_SHADOW, C_INNER, C_LEAF, C_TRI, C_TLAS, C_LIGHT, C_SHADED, C_ENV_NEE, C_ENV_MISS, C_TEX,
+       C_INNER_SH, C_LEAF_SH, C_TRI_SH, C_TLAS_SH, C_LIGHT_SH };
 
 }  // namespace lf

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -601,6 +602,38 @@ int lfcuda_get_stage_stats(lfcuda_ctx* ctx, LfStageStats* out) {
     }
     ctx->events.clear();
     *out = ctx->stats;
+    return 0;
+}
+
+int lfcuda_measure_read_bandwidth(lfcuda_ctx* ctx, size_t bytes, int32_t iters, double* gbps_out) {
+    if (!ctx || !gbps_out || bytes < 4096 || iters < 1) return fail(ctx, LFCUDA_EINVAL, "bad bandwidth probe arguments");
+    CK(cudaSetDevice(ctx->device));
+    size_t n4 = bytes / sizeof(float4);
+    float4* buf = nullptr; float* sink = nullptr;
+    CK(cudaMalloc((void**)&buf, n4 * sizeof(float4)));
+    CK(cudaMalloc((void**)&sink, sizeof(float)));
+    CK(cudaMemsetAsync(buf, 0, n4 * sizeof(float4), ctx->stream));
+    int blocks = ctx->prop.multiProcessorCount * 8;
+    // enough passes per launch that the launch itself is negligible (>= ~256 MB read per launch)
+    int passes = (int)std::max<size_t>(1, ((size_t)256 << 20) / (n4 * sizeof(float4)));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    launch_read_probe(ctx->stream, buf, n4, passes, sink, blocks);   // warm-up (fills L2 when the buffer fits)
+    double best = 0.0;
+    for (int it = 0; it < iters; it++) {
+        cudaEventRecord(a, ctx->stream);
+        launch_read_probe(ctx->stream, buf, n4, passes, sink, blocks);
+        cudaEventRecord(b, ctx->stream);
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        double gbps = (double)n4 * sizeof(float4) * passes / (ms * 1e6);
+        if (gbps > best) best = gbps;
+        ctx->launches++;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    *gbps_out = best;
     return 0;
 }
 

@@ -156,6 +156,11 @@ class PathTracer:
         self._ck(self.lib.lfcuda_get_stage_stats(self.h, C.byref(s)), "lfcuda_get_stage_stats")
         return s.as_dict()
 
+    def measure_read_bandwidth(self, nbytes, iters=20):
+        g = C.c_double()
+        self._ck(self.lib.lfcuda_measure_read_bandwidth(self.h, int(nbytes), int(iters), C.byref(g)), "lfcuda_measure_read_bandwidth")
+        return float(g.value)
+
     def launch_count(self):
         n = C.c_uint64()
         self._ck(self.lib.lfcuda_get_launch_count(self.h, C.byref(n)), "lfcuda_get_launch_count")
@@ -165,6 +170,13 @@ class PathTracer:
 def algorithmic_bytes(c):
     """bytes the traversal must touch for the visit counts `c` (reference layout figures)."""
     return (60 * c["inner_visits"] + 12 * c["leaf_visits"] + 60 * c["tri_tests"] + 76 * c["tlas_visits"] + 60 * c["light_tests"])
+
+
+def algorithmic_bytes_split(c):
+    """(closest-hit bytes, shadow-ray bytes) of the traversal formula, for the extend and shadow kernels."""
+    sh = (60 * c["inner_visits_shadow"] + 12 * c["leaf_visits_shadow"] + 60 * c["tri_tests_shadow"] + 76 * c["tlas_visits_shadow"]
+          + 60 * c["light_tests_shadow"])
+    return algorithmic_bytes(c) - sh, sh
 
 
 def algorithmic_bytes_total(c):

@@ -315,7 +315,7 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
     if (o->scene.num_lights > 0) {   // #ifdef LIGHTS  (closest_hit.glsl:13-67, anyhit.glsl:11-46)
         for (int i = 0; i < o->scene.num_lights; i++) {
             Light L = fetchLight(o, i);
-            if (g.cnt) g.cnt->light_tests++;
+            if (g.cnt) { g.cnt->light_tests++; if (ANY) g.cnt->light_tests_shadow++; }
             vec3 u = L.u, v = L.v;
             if (L.type == 0.f) {
                 vec3 normal = normalize(cross(u, v));
@@ -381,12 +381,12 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
         int leftIndex = (int)lr.x, rightIndex = (int)lr.y, leaf = (int)lr.z;
 
         if (leaf > 0) {   // BLAS leaf: closest_hit.glsl:108-147 / anyhit.glsl:87-116
-            if (g.cnt) g.cnt->leaf_visits++;
+            if (g.cnt) { g.cnt->leaf_visits++; if (ANY) g.cnt->leaf_visits_shadow++; }
             for (int i = 0; i < rightIndex; i++) {
                 int index = leftIndex + i;
                 const int32_t* vi = o->scene.vert_indices + 3 * (size_t)index;
                 vec4 v0 = vtx(o, vi[0]), v1 = vtx(o, vi[1]), v2 = vtx(o, vi[2]);
-                if (g.cnt) g.cnt->tri_tests++;
+                if (g.cnt) { g.cnt->tri_tests++; if (ANY) g.cnt->tri_tests_shadow++; }
                 vec3 p0 = {v0.x, v0.y, v0.z};
                 vec3 e0 = vec3{v1.x, v1.y, v1.z} - p0;
                 vec3 e1 = vec3{v2.x, v2.y, v2.z} - p0;
@@ -417,7 +417,7 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
                 }
             }
         } else if (leaf < 0) {   // TLAS leaf: closest_hit.glsl:148-166
-            if (g.cnt) g.cnt->tlas_visits++;
+            if (g.cnt) { g.cnt->tlas_visits++; if (ANY) g.cnt->tlas_visits_shadow++; }
             idx = leftIndex;
             const float* m = o->scene.transforms + 16 * (size_t)(-leaf - 1);
             for (int c = 0; c < 4; c++) temp_transform.c[c] = {m[4 * c + 0], m[4 * c + 1], m[4 * c + 2], m[4 * c + 3]};
@@ -431,7 +431,7 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
             currMatID = rightIndex;
             continue;
         } else {   // inner node: closest_hit.glsl:167-199
-            if (g.cnt) g.cnt->inner_visits++;
+            if (g.cnt) { g.cnt->inner_visits++; if (ANY) g.cnt->inner_visits_shadow++; }
             float le, re;
             leftHit = AABBIntersect(bvhTexel(o, leftIndex * 3 + 0), bvhTexel(o, leftIndex * 3 + 1), r_trans, &le);
             rightHit = AABBIntersect(bvhTexel(o, rightIndex * 3 + 0), bvhTexel(o, rightIndex * 3 + 1), r_trans, &re);
