@@ -108,7 +108,7 @@ def load_lfcuda():
     global _lfcuda
     if _lfcuda is not None:
         return _lfcuda
-    path = lib_path("liblfcuda.so")
+    path = os.environ.get("LF_LFCUDA_SO") or lib_path("liblfcuda.so")   # the override is for A/B experiments only
     if not os.path.exists(path):
         raise LfCudaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback for the path-tracing core)")

@@ -56,6 +56,15 @@ constexpr float kEPS = 0.001f;
 constexpr float kCullSlack = 1.0001f;
 
 LFD float4 ldg4(const float4* p) { return __ldg(p); }
+// 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100+): a 64-byte node costs 2 L1 lookups per lane instead of 4.
+// Used for the nodes only: on the 48-byte triangle records (256 + 128 bit) it measured slower than 3 x LDG.E.128.
+struct f8 { float4 lo, hi; };
+LFD f8 ldg8(const float4* p) {
+    f8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+}
 
 // ---------------------------------------------------------------------------------------------- RNG
 // globals.glsl:122-133.  State lives in registers inside a kernel, in PathSoA::rng between kernels.
@@ -153,15 +162,22 @@ LFD LightRec load_light(const DevScene& S, int i) {
 }
 
 // ---------------------------------------------------------------------------------------------- traversal
-// closest_hit.glsl:7-205 (ANY = false) and anyhit.glsl:7-173 (ANY = true) over the re-packed arrays.
+// closest_hit.glsl:7-205 (ANY = false) and anyhit.glsl:7-173 (ANY = true) over the re-packed arrays, cut into the
+// steps both kernel organisations share: per-thread walk (trace(), megakernel) and warp-cooperative walk (k_trace).
 // `stk` is this thread's column of the CTA's shared-memory stack (stride = kBlockThreads ints).
-template <bool ANY, bool CULL, bool COUNT>
-LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* stk, DevCounters* cnt) {
-    float t = kINF;
-    if (!ANY) { hit.light = -1; hit.tri = -1; hit.inst = -1; hit.mat = -1; hit.u = hit.v = 0.f; hit.lpdf = 0.f; }
-    bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
 
-    // Analytic lights first (closest_hit.glsl:13-67, anyhit.glsl:11-46)
+struct Walk {                  // traversal registers of one ray
+    f3 o, d, idir;             // ray in the current space (world or instance-local), 1/d
+    int ref, sp;               // current node reference, stack pointer
+    int curInst, curMat;
+    bool inBlas;
+};
+
+LFD void hit_clear(Hit& hit) { hit.light = -1; hit.tri = -1; hit.inst = -1; hit.mat = -1; hit.u = hit.v = 0.f; hit.lpdf = 0.f; hit.t = kINF; }
+
+// Analytic lights first (closest_hit.glsl:13-67, anyhit.glsl:11-46).  ANY: returns true when a light blocks the ray.
+template <bool ANY, bool COUNT>
+LFD bool test_lights(const DevScene& S, const Ray& r, float maxDist, Hit& hit, DevCounters* cnt) {
     for (int i = 0; i < S.num_lights; i++) {
         LightRec L = load_light(S, i);
         bump<COUNT>(cnt, C_LIGHT); if (ANY) bump<COUNT>(cnt, C_LIGHT_SH);
@@ -171,10 +187,10 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
             if (ANY) { if (d > 0.0f && d < maxDist) return true; }
             else {
                 if (d < 0.f) d = kINF;
-                if (d < t) {
-                    t = d;
+                if (d < hit.t) {
+                    hit.t = d;
                     float cosTheta = dot(-r.d, L.normal);
-                    hit.lpdf = (t * t) / (L.area * cosTheta);
+                    hit.lpdf = (d * d) / (L.area * cosTheta);
                     hit.light = i;
                 }
             }
@@ -184,106 +200,129 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
             if (ANY) { if (d > 0.0f && d < maxDist) return true; }
             else {
                 if (d < 0.f) d = kINF;
-                if (d < t) { t = d; hit.lpdf = (t * t) / L.area; hit.light = i; }
+                if (d < hit.t) { hit.t = d; hit.lpdf = (d * d) / L.area; hit.light = i; }
             }
         }
     }
+    return false;
+}
 
-    int sp = 0;
-    stk[0] = kRefSentinel; sp = 1;                // stack[ptr++] = -1
-    int ref = S.top_ref;
-    bool inBlas = false;
-    int curInst = -1, curMat = 0;
-    f3 o = r.o, d = r.d;
-    f3 idir = mk3(1.0f) / d;
+LFD void walk_begin(const DevScene& S, const Ray& r, Walk& w, int* stk) {
+    stk[0] = kRefSentinel;                        // stack[ptr++] = -1
+    w.sp = 1;
+    w.ref = S.top_ref;
+    w.inBlas = false;
+    w.curInst = -1; w.curMat = 0;
+    w.o = r.o; w.d = r.d;
+    w.idir = mk3(1.0f) / r.d;
+}
 
-    while (true) {
-        if (ref == kRefSentinel) {                // `idx < 0`: end of a BLAS (restore the world ray) or of the walk
-            if (!inBlas) break;
-            inBlas = false;
-            o = r.o; d = r.d; idir = mk3(1.0f) / d;
-            ref = stk[(--sp) * kBlockThreads];
-            continue;
+// inverse(M) * vec4(origin, 1) and * vec4(direction, 0), summed column by column like the GLSL mat4*vec4 (closest_hit.glsl:159-160)
+LFD void to_instance(const float4 r0, const float4 r1, const float4 r2, const Ray& r, f3& o, f3& d) {
+    o = mk3(((r0.x * r.o.x + r0.y * r.o.y) + r0.z * r.o.z) + r0.w * 1.0f,
+            ((r1.x * r.o.x + r1.y * r.o.y) + r1.z * r.o.z) + r1.w * 1.0f,
+            ((r2.x * r.o.x + r2.y * r.o.y) + r2.z * r.o.z) + r2.w * 1.0f);
+    d = mk3(((r0.x * r.d.x + r0.y * r.d.y) + r0.z * r.d.z) + r0.w * 0.0f,
+            ((r1.x * r.d.x + r1.y * r.d.y) + r1.z * r.d.z) + r1.w * 0.0f,
+            ((r2.x * r.d.x + r2.y * r.d.y) + r2.z * r.d.z) + r2.w * 0.0f);
+}
+
+// One step of the walk for a reference that is not a triangle leaf: inner node, instance entry, or stack marker.
+// Returns false when the walk is over (marker popped at world level).  `limit` = current best t (closest) or maxDist (any).
+template <bool ANY, bool CULL, bool COUNT>
+LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, int* stk, DevCounters* cnt) {
+    if (w.ref >= 0) {                             // inner node (closest_hit.glsl:167-199)
+        bump<COUNT>(cnt, C_INNER); if (ANY) bump<COUNT>(cnt, C_INNER_SH);
+        const float4* n = S.nodes + (size_t)4 * w.ref;
+#ifndef LF_NODE_LDG128   // 256-bit node loads: extend -4.6 %, shadow -3 % on C2 against 4 x LDG.E.128 (A/B on one box)
+        f8 na = ldg8(n), nb = ldg8(n + 2);
+        float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+#else
+        float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3);
+#endif
+        float le, re;
+        float leftHit = AABBIntersect(mk3(n0.x, n0.y, n0.z), mk3(n0.w, n1.x, n1.y), w.o, w.idir, le);
+        float rightHit = AABBIntersect(mk3(n1.z, n1.w, n2.x), mk3(n2.y, n2.z, n2.w), w.o, w.idir, re);
+        int leftRef = __float_as_int(n3.x), rightRef = __float_as_int(n3.y);
+        bool lok = leftHit > 0.0f, rok = rightHit > 0.0f;
+        if (CULL) {
+            float lim = limit * kCullSlack;
+            lok = lok && !(le > lim);
+            rok = rok && !(re > lim);
         }
-        if (ref >= 0) {                           // inner node (closest_hit.glsl:167-199)
-            bump<COUNT>(cnt, C_INNER); if (ANY) bump<COUNT>(cnt, C_INNER_SH);
-            const float4* n = S.nodes + (size_t)4 * ref;
-            float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3);
-            float le, re;
-            float leftHit = AABBIntersect(mk3(n0.x, n0.y, n0.z), mk3(n0.w, n1.x, n1.y), o, idir, le);
-            float rightHit = AABBIntersect(mk3(n1.z, n1.w, n2.x), mk3(n2.y, n2.z, n2.w), o, idir, re);
-            int leftRef = __float_as_int(n3.x), rightRef = __float_as_int(n3.y);
-            bool lok = leftHit > 0.0f, rok = rightHit > 0.0f;
-            if (CULL) {
-                float lim = (ANY ? maxDist : t) * kCullSlack;
-                lok = lok && !(le > lim);
-                rok = rok && !(re > lim);
-            }
-            if (lok && rok) {
-                int deferred;
-                if (leftHit > rightHit) { ref = rightRef; deferred = leftRef; }
-                else { ref = leftRef; deferred = rightRef; }
-                stk[(sp++) * kBlockThreads] = deferred;
-                continue;
-            }
-            if (lok) { ref = leftRef; continue; }
-            if (rok) { ref = rightRef; continue; }
-        } else if (ref & kRefTlasBit) {           // TLAS leaf (closest_hit.glsl:148-166)
-            bump<COUNT>(cnt, C_TLAS); if (ANY) bump<COUNT>(cnt, C_TLAS_SH);
-            curInst = ref_instance(ref);
-            const float4* ip = S.inst + (size_t)kInstStride * curInst;
-            float4 r0 = ldg4(ip), r1 = ldg4(ip + 1), r2 = ldg4(ip + 2), meta = ldg4(ip + 3);
-            // inverse(M) * vec4(origin, 1) and * vec4(direction, 0), summed column by column like the GLSL mat4*vec4
-            o = mk3(((r0.x * r.o.x + r0.y * r.o.y) + r0.z * r.o.z) + r0.w * 1.0f,
-                    ((r1.x * r.o.x + r1.y * r.o.y) + r1.z * r.o.z) + r1.w * 1.0f,
-                    ((r2.x * r.o.x + r2.y * r.o.y) + r2.z * r.o.z) + r2.w * 1.0f);
-            d = mk3(((r0.x * r.d.x + r0.y * r.d.y) + r0.z * r.d.z) + r0.w * 0.0f,
-                    ((r1.x * r.d.x + r1.y * r.d.y) + r1.z * r.d.z) + r1.w * 0.0f,
-                    ((r2.x * r.d.x + r2.y * r.d.y) + r2.z * r.d.z) + r2.w * 0.0f);
-            idir = mk3(1.0f) / d;
-            stk[(sp++) * kBlockThreads] = kRefSentinel;
-            inBlas = true;
-            curMat = __float_as_int(meta.y);
-            ref = __float_as_int(meta.x);
-            continue;
-        } else {                                  // BLAS leaf (closest_hit.glsl:108-147, anyhit.glsl:87-116)
-            bump<COUNT>(cnt, C_LEAF); if (ANY) bump<COUNT>(cnt, C_LEAF_SH);
-            int first = ref_leaf_first(ref), count = ref_leaf_count(ref);
-            for (int i = 0; i < count; i++) {
-                const float4* tp = S.tris + (size_t)3 * (first + i);
-                float4 q0 = ldg4(tp), q1 = ldg4(tp + 1), q2 = ldg4(tp + 2);
-                bump<COUNT>(cnt, C_TRI); if (ANY) bump<COUNT>(cnt, C_TRI_SH);
-                f3 e0 = mk3(q1.x, q1.y, q1.z), e1 = mk3(q2.x, q2.y, q2.z);
-                f3 pv = cross(d, e1);
-                float det = dot(e0, pv);
-                f3 tv = o - mk3(q0.x, q0.y, q0.z);
-                f3 qv = cross(tv, e0);
-                float uu = dot(tv, pv) / det;
-                if (!(uu >= 0.f)) continue;
-                float vv = dot(d, qv) / det;
-                if (!(vv >= 0.f)) continue;
-                float tt = dot(e1, qv) / det;
-                float ww = 1.0f - uu - vv;
-                if (!(tt >= 0.f) || !(ww >= 0.f)) continue;
-                if (ANY) { if (tt < maxDist) return true; }
-                else if (tt < t) { t = tt; hit.u = uu; hit.v = vv; hit.tri = first + i; hit.inst = curInst; hit.mat = curMat; hit.light = -1; }
-            }
-        }
-        ref = stk[(--sp) * kBlockThreads];
+        if (lok && rok) {
+            bool swap = leftHit > rightHit;       // near child first, far child deferred (:172-184)
+            w.ref = swap ? rightRef : leftRef;
+            stk[(w.sp++) * kBlockThreads] = swap ? leftRef : rightRef;
+        } else if (lok) w.ref = leftRef;
+        else if (rok) w.ref = rightRef;
+        else w.ref = stk[(--w.sp) * kBlockThreads];
+        return true;
     }
-    if (ANY) return false;
-    hit.t = t;
+    if (w.ref == kRefSentinel) {                  // `idx < 0`: end of a BLAS (restore the world ray) or of the walk
+        if (!w.inBlas) return false;
+        w.inBlas = false;
+        w.o = r.o; w.d = r.d; w.idir = mk3(1.0f) / r.d;
+        w.ref = stk[(--w.sp) * kBlockThreads];
+        return true;
+    }
+    // TLAS leaf (closest_hit.glsl:148-166)
+    bump<COUNT>(cnt, C_TLAS); if (ANY) bump<COUNT>(cnt, C_TLAS_SH);
+    w.curInst = ref_instance(w.ref);
+    const float4* ip = S.inst + (size_t)kInstStride * w.curInst;
+    float4 r0 = ldg4(ip), r1 = ldg4(ip + 1), r2 = ldg4(ip + 2), meta = ldg4(ip + 3);
+    to_instance(r0, r1, r2, r, w.o, w.d);
+    w.idir = mk3(1.0f) / w.d;
+    stk[(w.sp++) * kBlockThreads] = kRefSentinel;
+    w.inBlas = true;
+    w.curMat = __float_as_int(meta.y);
+    w.ref = __float_as_int(meta.x);
+    return true;
+}
+
+// BLAS leaf (closest_hit.glsl:108-147, anyhit.glsl:87-116).  ANY: returns true at the first hit below maxDist.
+template <bool ANY, bool COUNT>
+LFD bool walk_leaf(const DevScene& S, const Walk& w, float maxDist, Hit& hit, DevCounters* cnt) {
+    bump<COUNT>(cnt, C_LEAF); if (ANY) bump<COUNT>(cnt, C_LEAF_SH);
+    const int first = ref_leaf_first(w.ref), count = ref_leaf_count(w.ref);
+    for (int i = 0; i < count; i++) {
+        const float4* tp = S.tris + (size_t)kTriStride * (first + i);
+        float4 q0 = ldg4(tp), q1 = ldg4(tp + 1), q2 = ldg4(tp + 2);
+        bump<COUNT>(cnt, C_TRI); if (ANY) bump<COUNT>(cnt, C_TRI_SH);
+        f3 e0 = mk3(q1.x, q1.y, q1.z), e1 = mk3(q2.x, q2.y, q2.z);
+        f3 pv = cross(w.d, e1);
+        float det = dot(e0, pv);
+        f3 tv = w.o - mk3(q0.x, q0.y, q0.z);
+        // The shader accepts iff u = a/det, v = b/det, t = c/det and w = 1-u-v are all >= 0 (:121-131).  A quotient of
+        // two non-zero floats of strictly opposite sign is negative, so those cases are rejected from the sign of the
+        // product, before any division; everything else takes the shader's exact arithmetic.
+        float a = dot(tv, pv);
+        if (a * det < 0.f) continue;
+        f3 qv = cross(tv, e0);
+        float b = dot(w.d, qv);
+        if (b * det < 0.f) continue;
+        float c = dot(e1, qv);
+        if (c * det < 0.f) continue;
+        float uu = a / det;
+        float vv = b / det;
+        float ww = 1.0f - uu - vv;
+        if (!(uu >= 0.f) || !(vv >= 0.f) || !(ww >= 0.f)) continue;
+        float tt = c / det;
+        if (!(tt >= 0.f)) continue;
+        if (ANY) { if (tt < maxDist) return true; }
+        else if (tt < hit.t) { hit.t = tt; hit.u = uu; hit.v = vv; hit.tri = first + i; hit.inst = w.curInst; hit.mat = w.curMat; hit.light = -1; }
+    }
+    return false;
+}
+
+// state.fhp = vec3(M * vec4(r_trans.origin + r_trans.direction * t, 1)) (closest_hit.glsl:139,143) for the final hit
+LFD void hit_point(const DevScene& S, const Ray& r, Hit& hit) {
     if (hit.light < 0 && hit.tri >= 0) {
-        // state.fhp = vec3(M * vec4(r_trans.origin + r_trans.direction * t, 1)) (closest_hit.glsl:139,143)
         const float4* ip = S.inst + (size_t)kInstStride * hit.inst;
         float4 r0 = ldg4(ip), r1 = ldg4(ip + 1), r2 = ldg4(ip + 2);
-        f3 oo = mk3(((r0.x * r.o.x + r0.y * r.o.y) + r0.z * r.o.z) + r0.w * 1.0f,
-                    ((r1.x * r.o.x + r1.y * r.o.y) + r1.z * r.o.z) + r1.w * 1.0f,
-                    ((r2.x * r.o.x + r2.y * r.o.y) + r2.z * r.o.z) + r2.w * 1.0f);
-        f3 dd = mk3(((r0.x * r.d.x + r0.y * r.d.y) + r0.z * r.d.z) + r0.w * 0.0f,
-                    ((r1.x * r.d.x + r1.y * r.d.y) + r1.z * r.d.z) + r1.w * 0.0f,
-                    ((r2.x * r.d.x + r2.y * r.d.y) + r2.z * r.d.z) + r2.w * 0.0f);
-        f3 ph = oo + dd * t;
+        f3 oo, dd;
+        to_instance(r0, r1, r2, r, oo, dd);
+        f3 ph = oo + dd * hit.t;
         float4 m0 = ldg4(ip + 4), m1 = ldg4(ip + 5), m2 = ldg4(ip + 6);
         hit.fhp = mk3(((m0.x * ph.x + m0.y * ph.y) + m0.z * ph.z) + m0.w * 1.0f,
                       ((m1.x * ph.x + m1.y * ph.y) + m1.z * ph.z) + m1.w * 1.0f,
@@ -291,7 +330,29 @@ LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* st
     } else {
         hit.fhp = mk3(0.f);
     }
-    return t != kINF;
+}
+
+// Per-thread walk (megakernel).  Closest: fills `hit`, returns t != INFINITY.  Any: returns true when occluded.
+template <bool ANY, bool CULL, bool COUNT>
+LFD bool trace(const DevScene& S, const Ray& r, float maxDist, Hit& hit, int* stk, DevCounters* cnt) {
+    if (!ANY) hit_clear(hit);
+    bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
+    if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return true;
+    Walk w;
+    walk_begin(S, r, w, stk);
+    for (;;) {
+        bool more = true;
+        while (w.ref >= 0 || (w.ref & kRefTlasBit)) {
+            more = walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+            if (!more) break;
+        }
+        if (!more) break;
+        if (walk_leaf<ANY, COUNT>(S, w, maxDist, hit, cnt)) return true;
+        w.ref = stk[(--w.sp) * kBlockThreads];
+    }
+    if (ANY) return false;
+    hit_point(S, r, hit);
+    return hit.t != kINF;
 }
 
 // ---------------------------------------------------------------------------------------------- sampling.glsl
@@ -389,13 +450,16 @@ LFD void sampleOneLight(const LightRec& light, int numLights, f3 surfacePos, Rng
 }
 
 // ---- environment map: GL sampling rules restated (Renderer.cpp:163-185: hdrTex LINEAR, tables NEAREST, REPEAT)
+// GL_REPEAT texel wrap: full modulo for arbitrary texture coordinates (material textures), and a branch-free
+// two-select form for indices known to lie in [-n, 2n) (env-map lookups: u, v in [0, 1], bilinear neighbours).
 LFD int wrapi(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
-LFD int nearestIdx(float u, int n) { return wrapi((int)floorf(u * (float)n), n); }
+LFD int wrapn(int i, int n) { i += (i < 0) ? n : 0; i -= (i >= n) ? n : 0; return i; }
+LFD int nearestIdx(float u, int n) { return wrapn((int)floorf(u * (float)n), n); }
 LFD f3 hdrLinear(const DevScene& S, float u, float v) {
     float x = u * (float)S.hdr_w - 0.5f, y = v * (float)S.hdr_h - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float wx = x - fx, wy = y - fy;
-    int x0 = wrapi((int)fx, S.hdr_w), x1 = wrapi((int)fx + 1, S.hdr_w), y0 = wrapi((int)fy, S.hdr_h), y1 = wrapi((int)fy + 1, S.hdr_h);
+    int x0 = wrapn((int)fx, S.hdr_w), x1 = wrapn((int)fx + 1, S.hdr_w), y0 = wrapn((int)fy, S.hdr_h), y1 = wrapn((int)fy + 1, S.hdr_h);
     f3 a = xyz(tex2D<float4>(S.hdr_tex, (float)x0, (float)y0)), b = xyz(tex2D<float4>(S.hdr_tex, (float)x1, (float)y0));
     f3 c = xyz(tex2D<float4>(S.hdr_tex, (float)x0, (float)y1)), e = xyz(tex2D<float4>(S.hdr_tex, (float)x1, (float)y1));
     f3 top = a + (b - a) * wx, bot = c + (e - c) * wx;
@@ -603,7 +667,7 @@ LFD void Onb(f3 N, f3& T, f3& B) {   // pathtrace.glsl:7-13
 template <bool COUNT>
 LFD void load_surface(const DevScene& S, const Hit& hit, f3 rdir, Surf& s, DevCounters* cnt) {
     const float4* np = S.trinrm + (size_t)3 * hit.tri;
-    const float4* tp = S.tris + (size_t)3 * hit.tri;
+    const float4* tp = S.tris + (size_t)kTriStride * hit.tri;
     float4 n1 = ldg4(np), n2 = ldg4(np + 1), n3 = ldg4(np + 2);
     float bw = 1.0f - hit.u - hit.v, bu = hit.u, bv = hit.v;      // state.bary = uvt.wxy
     float tu0 = ldg4(tp).w, tu1 = ldg4(tp + 1).w, tu2 = ldg4(tp + 2).w;   // tempTexCoords (closest_hit.glsl:141)

@@ -194,36 +194,146 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
     }
 }
 
-// ---------------------------------------------------------------------------------------------- extend
-template <bool CULL, bool COUNT, int STACK>
-__global__ void __launch_bounds__(kBlockThreads) k_extend(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
-                                                        int* cursor, DevCounters* cnt) {
+// ---------------------------------------------------------------------------------------------- extend / shadow
+// Warp-cooperative persistent traversal, shared by the closest-hit (extend) and any-hit (shadow) stages.
+//   * Every lane keeps one ray's walk in registers; the loop body is warp-uniform and alternates two phases:
+//     (1) each lane steps through inner nodes / instance entries until it holds a triangle leaf, (2) the leaves are
+//     tested together.  The single-loop version ran the leaf code with 2 of 32 lanes active; a speculative variant
+//     (postponed leaf, Aila & Laine) was measured too and lost: with distance culling the stale t costs 78 % more node
+//     visits (profiles/README.md).
+//   * Lanes whose ray is finished are refilled from the queue as soon as kRefillMin of them are idle: one atomicAdd
+//     per refill, positions by ballot prefix, so a warp never idles behind its longest ray.
+//   * Shadow work item = path slot with up to two NEE rays (env, analytic light), traced one after the other by the
+//     same lane; radiance += (visible sum) * throughput is applied when the second is done (pathtrace.glsl:266).
+constexpr int kRefillMin = 8;      // idle lanes that trigger a refill from the queue
+constexpr int kLeafGather = 3;     // leaf phase starts when live lanes / kLeafGather are parked at a leaf
+
+template <bool ANY, bool CULL, bool COUNT, int STACK>
+__global__ void __launch_bounds__(kBlockThreads) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
+                                                       int* cursor, DevCounters* cnt) {
     __shared__ int stack[STACK * kBlockThreads];
+    __shared__ float wray[6 * kBlockThreads];           // world-space ray of each lane (restored when a BLAS is left)
     int* stk = stack + threadIdx.x;
+    float* wr = wray + threadIdx.x;
     const int count = *countp;
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        int i = base + lane;
-        if (i < count) {
-            int s = queue[i];
-            Ray r; r.o = xyz(A.ray_o[s]); r.d = xyz(A.ray_d[s]);
-            Hit h;
-            trace<false, CULL, COUNT>(S, r, 0.f, h, stk, cnt);
-            A.hit_f[s] = make_float4(h.t, h.u, h.v, h.lpdf);
-            A.hit_i[s] = make_int4(h.tri, h.inst, h.light, h.mat);
-            A.hit_p[s] = make_float4(h.fhp.x, h.fhp.y, h.fhp.z, 0.f);
+    const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    bool alive = false, exhausted = false;
+    int slot = -1;
+    Walk w;
+    Hit hit;
+    float maxDist = 0.f;
+    int shMask = 0, shPhase = 0;                        // shadow: requested rays (bit 0 env, bit 1 light), ray being traced
+    f3 Li = mk3(0.0f);
+    w.ref = kRefSentinel; w.sp = 0; w.inBlas = false; w.curInst = -1; w.curMat = 0;
+    w.o = w.d = w.idir = mk3(0.f);
+    hit_clear(hit);
+
+    auto world_ray = [&]() { Ray r; r.o = mk3(wr[0], wr[kBlockThreads], wr[2 * kBlockThreads]);
+                             r.d = mk3(wr[3 * kBlockThreads], wr[4 * kBlockThreads], wr[5 * kBlockThreads]); return r; };
+    // start the walk of ray r; returns false when the ray is already decided (ANY: an analytic light blocks it)
+    auto begin_ray = [&](const Ray& r) -> bool {
+        wr[0] = r.o.x; wr[kBlockThreads] = r.o.y; wr[2 * kBlockThreads] = r.o.z;
+        wr[3 * kBlockThreads] = r.d.x; wr[4 * kBlockThreads] = r.d.y; wr[5 * kBlockThreads] = r.d.z;
+        if (!ANY) hit_clear(hit);
+        bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
+        if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return false;
+        walk_begin(S, r, w, stk);
+        return true;
+    };
+    // shadow: load NEE ray `phase` of the slot
+    auto shadow_ray = [&](int phase) {
+        float4 so = A.sh_o[slot];
+        float4 dd = phase == 0 ? A.sh_d0[slot] : A.sh_d1[slot];
+        Ray r; r.o = xyz(so); r.d = xyz(dd);
+        maxDist = dd.w;
+        return r;
+    };
+
+    for (;;) {
+        // ---- refill idle lanes
+        unsigned idle = __ballot_sync(FULL, !alive);
+        if (!exhausted && (idle == FULL || __popc(idle) >= kRefillMin)) {
+            int n = __popc(idle), base = 0;
+            if (lane == 0) base = atomicAdd(cursor, n);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + n >= count) exhausted = true;
+            int idx = base + __popc(idle & ltmask);
+            if (!alive && idx < count) {
+                slot = queue[idx];
+                alive = true;
+                Ray r;
+                if (ANY) {
+                    shMask = __float_as_int(A.sh_o[slot].w);
+                    shPhase = (shMask & 1) ? 0 : 1;
+                    Li = mk3(0.0f);
+                    r = shadow_ray(shPhase);
+                } else {
+                    r.o = xyz(A.ray_o[slot]); r.d = xyz(A.ray_d[slot]);
+                }
+                if (!begin_ray(r)) { w.ref = kRefSentinel; w.inBlas = false; hit.light = 0; }   // decided: occluded by a light
+                else if (ANY) hit.light = -1;
+            }
+        }
+        if (!__any_sync(FULL, alive)) break;
+
+        // ---- phase 1: every lane steps through inner nodes / instance entries; a lane that reaches a triangle leaf
+        // parks there.  The phase ends when a third of the live lanes are parked (or nobody can step): leaves are then
+        // tested by many lanes at once, while the walk itself never waits for the slowest lane.
+        bool rayDone = false;
+        const int liveLanes = __popc(__ballot_sync(FULL, alive));
+        for (;;) {
+            const bool atLeaf = alive && !rayDone && w.ref < 0 && !(w.ref & kRefTlasBit);
+            const bool canStep = alive && !rayDone && !atLeaf;
+            const unsigned leafMask = __ballot_sync(FULL, atLeaf), stepMask = __ballot_sync(FULL, canStep);
+            if (stepMask == 0u || __popc(leafMask) * kLeafGather >= liveLanes) break;
+            if (canStep) {
+                Ray r;
+                if (w.ref < 0) r = world_ray();              // only instance entries / exits read the world ray
+                if (!walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt)) rayDone = true;
+            }
+        }
+        // ---- phase 2: the parked leaves' triangles, together
+        if (alive && !rayDone && w.ref < 0 && !(w.ref & kRefTlasBit)) {
+            if (walk_leaf<ANY, COUNT>(S, w, maxDist, hit, cnt)) { rayDone = true; hit.light = 0; }      // ANY: occluded
+            else w.ref = stk[(--w.sp) * kBlockThreads];
         }
         __syncwarp();
+        // ---- finished rays: write the result; shadow lanes go on with their second ray
+        if (rayDone) {
+            if (!ANY) {
+                Ray r = world_ray();
+                hit_point(S, r, hit);
+                A.hit_f[slot] = make_float4(hit.t, hit.u, hit.v, hit.lpdf);
+                A.hit_i[slot] = make_int4(hit.tri, hit.inst, hit.light, hit.mat);
+                A.hit_p[slot] = make_float4(hit.fhp.x, hit.fhp.y, hit.fhp.z, 0.f);
+                alive = false;
+            } else {
+                bool occluded = hit.light == 0;
+                if (!occluded) Li = Li + xyz(shPhase == 0 ? A.sh_c0[slot] : A.sh_c1[slot]);
+                if (shPhase == 0 && (shMask & 2)) {
+                    shPhase = 1;
+                    Ray r = shadow_ray(1);
+                    if (!begin_ray(r)) { w.ref = kRefSentinel; w.inBlas = false; hit.light = 0; }
+                    else hit.light = -1;
+                } else {
+                    float4 ra = A.rad[slot];
+                    f3 rad = xyz(ra) + Li * xyz(A.sh_T[slot]);           // radiance += DirectLight(r, state) * throughput
+                    A.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.f);
+                    alive = false;
+                }
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- shade
+#ifndef LF_SHADE_MINBLOCKS
+#define LF_SHADE_MINBLOCKS 8   // 64 registers: measured best on C2 (4: 137 ms, 8: 113 ms, 10: 123 ms, 12: 128 ms per 8 steps); the kernel is latency-bound
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shade(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
+__global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
     const int* queue = Q.active[depth & 1];
     int* next = Q.active[(depth + 1) & 1];
     const int count = Q.counts[0 * Q.stride + depth];
@@ -259,45 +369,6 @@ __global__ void __launch_bounds__(128) k_shade(DevScene S, DevParams P, PathSoA 
         }
         queue_push(next, nextCount, alive, s);
         queue_push(Q.shadow, shadowCount, wantShadow, s);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- shadow
-template <bool CULL, bool COUNT, int STACK>
-__global__ void __launch_bounds__(kBlockThreads) k_shadow(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
-                                                        int* cursor, DevCounters* cnt) {
-    __shared__ int stack[STACK * kBlockThreads];
-    int* stk = stack + threadIdx.x;
-    const int count = *countp;
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        int i = base + lane;
-        if (i < count) {
-            int s = queue[i];
-            float4 so = A.sh_o[s];
-            int mask = __float_as_int(so.w);
-            Ray r; r.o = xyz(so);
-            Hit dummy;
-            f3 Li = mk3(0.0f);
-            if (mask & 1) {
-                float4 d0 = A.sh_d0[s];
-                r.d = xyz(d0);
-                if (!trace<true, CULL, COUNT>(S, r, d0.w, dummy, stk, cnt)) Li = Li + xyz(A.sh_c0[s]);
-            }
-            if (mask & 2) {
-                float4 d1 = A.sh_d1[s];
-                r.d = xyz(d1);
-                if (!trace<true, CULL, COUNT>(S, r, d1.w, dummy, stk, cnt)) Li = Li + xyz(A.sh_c1[s]);
-            }
-            float4 ra = A.rad[s];
-            f3 rad = xyz(ra) + Li * xyz(A.sh_T[s]);              // radiance += DirectLight(r, state) * throughput
-            A.rad[s] = make_float4(rad.x, rad.y, rad.z, 0.f);
-        }
-        __syncwarp();
     }
 }
 
@@ -430,8 +501,8 @@ void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int pa
 // ---------------------------------------------------------------------------------------------- launchers
 template <bool CULL, bool COUNT, int STACK>
 static void launch_trace_kernels_t(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
-    if (which == 0) k_extend<CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
-    else k_shadow<CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+    if (which == 0) k_trace<false, CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+    else k_trace<true, CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
 }
 template <bool CULL, bool COUNT>
 static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {

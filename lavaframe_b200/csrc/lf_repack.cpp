@@ -177,14 +177,14 @@ bool repack_instances(const float* nodes, int num_nodes, int top_index, const fl
                       PackedScene& out, std::string& err) {
     build_instances(transforms, num_instances, out);
     NodeView nv{nodes, num_nodes};
-    return build_nodes(nv, top_index, num_instances, (int)(out.tris.size() / 3), out, err);
+    return build_nodes(nv, top_index, num_instances, (int)(out.tris.size() / kTriStride), out, err);
 }
 
 bool repack_scene(const LfSceneView& v, PackedScene& out, std::string& err) {
     if (!v.bvh_nodes || v.num_nodes <= 0 || !v.vert_indices || !v.vertices_uvx || !v.normals_uvy || !v.transforms || !v.materials ||
         v.num_instances <= 0 || v.num_materials <= 0) { err = "scene view has empty mandatory arrays"; return false; }
     // triangles in leaf order
-    out.tris.resize((size_t)3 * v.num_tri_refs);
+    out.tris.assign((size_t)kTriStride * v.num_tri_refs, f4(0, 0, 0, 0));
     out.trinrm.resize((size_t)3 * v.num_tri_refs);
     out.tri_vx.resize(v.num_tri_refs);
     for (int i = 0; i < v.num_tri_refs; i++) {
@@ -194,9 +194,9 @@ bool repack_scene(const LfSceneView& v, PackedScene& out, std::string& err) {
         const float* a = v.vertices_uvx + 4 * (size_t)vi[0];
         const float* b = v.vertices_uvx + 4 * (size_t)vi[1];
         const float* c = v.vertices_uvx + 4 * (size_t)vi[2];
-        out.tris[3 * (size_t)i + 0] = f4(a[0], a[1], a[2], a[3]);
-        out.tris[3 * (size_t)i + 1] = f4(b[0] - a[0], b[1] - a[1], b[2] - a[2], b[3]);   // e0 = v1 - v0 (closest_hit.glsl:119)
-        out.tris[3 * (size_t)i + 2] = f4(c[0] - a[0], c[1] - a[1], c[2] - a[2], c[3]);   // e1 = v2 - v0 (:120)
+        out.tris[kTriStride * (size_t)i + 0] = f4(a[0], a[1], a[2], a[3]);
+        out.tris[kTriStride * (size_t)i + 1] = f4(b[0] - a[0], b[1] - a[1], b[2] - a[2], b[3]);   // e0 = v1 - v0 (closest_hit.glsl:119)
+        out.tris[kTriStride * (size_t)i + 2] = f4(c[0] - a[0], c[1] - a[1], c[2] - a[2], c[3]);   // e1 = v2 - v0 (:120)
         for (int k = 0; k < 3; k++) {
             const float* nn = v.normals_uvy + 4 * (size_t)vi[k];
             out.trinrm[3 * (size_t)i + k] = f4(nn[0], nn[1], nn[2], nn[3]);

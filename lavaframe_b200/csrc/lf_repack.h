@@ -10,7 +10,7 @@ namespace lf {
 
 struct PackedScene {
     std::vector<float4> nodes;      // 4 per inner node
-    std::vector<float4> tris;       // 3 per triangle ref
+    std::vector<float4> tris;       // kTriStride per triangle ref
     std::vector<float4> trinrm;     // 3 per triangle ref
     std::vector<int>    tri_vx;
     std::vector<float4> inst;       // kInstStride per instance

@@ -8,8 +8,8 @@
 //                        IS, so the child's own LRLeaf texel (closest_hit.glsl:102) is never fetched:
 //                          ref >= 0                      inner node, index into `nodes` (x4 float4)
 //                          ref <  0, bit 30 clear        BLAS leaf: bits 0-23 first triangle ref, bits 24-29 count-1
-//                          ref <  0, bit 30 set          TLAS leaf: bits 0-23 instance index
-//   triangle (48 B)    : v0|u0, e0=v1-v0|u1, e1=v2-v0|u2 in BVH leaf order (the vertIndices indirection of
+//                          ref <  0, bit 30 set          TLAS leaf: bits 0-23 instance index (-1 = stack sentinel)
+//   triangle (64 B)    : v0|u0, e0=v1-v0|u1, e1=v2-v0|u2, pad, in BVH leaf order (the vertIndices indirection of
 //                        closest_hit.glsl:113-117 is resolved at upload; e0/e1 are the same fp32 subtractions
 //                        the shader does per test, :119-120)
 //   triangle normals   : n0|v0, n1|v1, n2|v2 in the same order (pathtrace.glsl:19-21)
@@ -27,8 +27,9 @@ namespace lf {
 
 constexpr int   kRefLeafBit   = int(0x80000000u);
 constexpr int   kRefTlasBit   = 0x40000000;
-constexpr int   kRefSentinel  = 0x7fffffff;     // the reference's "-1" stack marker (closest_hit.glsl:72,162)
+constexpr int   kRefSentinel  = -1;             // the reference's "-1" stack marker (closest_hit.glsl:72,162); TLAS bit set
 constexpr int   kMaxLeafTris  = 64;
+constexpr int   kTriStride    = 4;              // float4 per triangle record (3 used; 64-byte records keep 256-bit loads aligned)
 constexpr int   kInstStride   = 10;             // float4 per instance record
 constexpr int   kLightStride  = 7;              // float4 per light record
 constexpr int   kBlockThreads = 128;            // threads per CTA of the traversal kernels
@@ -39,11 +40,11 @@ __host__ __device__ inline int  ref_leaf_first(int r) { return r & 0x00ffffff; }
 __host__ __device__ inline int  ref_leaf_count(int r) { return ((r >> 24) & 0x3f) + 1; }
 __host__ __device__ inline int  ref_instance(int r) { return r & 0x00ffffff; }
 inline int make_blas_leaf_ref(int first, int count) { return kRefLeafBit | ((count - 1) << 24) | first; }
-inline int make_tlas_leaf_ref(int inst) { return kRefLeafBit | kRefTlasBit | inst; }
+inline int make_tlas_leaf_ref(int inst) { return kRefLeafBit | kRefTlasBit | inst; }   // never -1: inst < 2^24
 
 struct DevScene {
     const float4* nodes;        // 4 per inner node
-    const float4* tris;         // 3 per triangle ref
+    const float4* tris;         // kTriStride per triangle ref
     const float4* trinrm;       // 3 per triangle ref
     const int*    tri_vx;       // vertIndices[ref].x (primary-hit probe only)
     const float4* inst;         // kInstStride per instance
