@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--workload", default="c2_full", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--kernel-mode", type=int, default=0, help="0 wavefront (default), 1 megakernel")
+    ap.add_argument("--frames-in-flight", type=int, default=0, help="pixel-sample frames per wavefront batch (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-llvmpipe", action="store_true")
     args = ap.parse_args()
@@ -238,7 +239,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     pt.set_stream(stream.cuda_stream)
-    pt.upload_pack(pack, kernel_mode=args.kernel_mode)
+    pt.upload_pack(pack, kernel_mode=args.kernel_mode, frames_in_flight=args.frames_in_flight)
     W, H = pt.params.width, pt.params.height
     S, K, Wm = args.spp_per_step, args.steps, args.warmup
     npix = W * H

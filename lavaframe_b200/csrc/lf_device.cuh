@@ -9,6 +9,7 @@
 #pragma once
 
 #include "lf_types.h"
+#include "lf_math.cuh"
 
 namespace lf {
 
@@ -16,6 +17,13 @@ namespace lf {
 struct f3 { float x, y, z; };
 
 #define LFD __device__ __forceinline__
+// The shade kernel is instruction-cache bound (`no_instruction` is its top stall).  Two remedies were measured: the
+// transcendental functions out of line (lf_math.cuh, kept: -5 %) and the BSDF lobes / DisneyEval out of line (rejected).
+#ifdef LF_OUTLINE_EVAL   // measured on C2: outlining the BSDF lobes / DisneyEval costs 40 % in the shade kernel (struct traffic through the stack)
+#define LFN __device__ __noinline__
+#else
+#define LFN __device__ __forceinline__
+#endif
 
 LFD f3 mk3(float a, float b, float c) { f3 r; r.x = a; r.y = b; r.z = c; return r; }
 LFD f3 mk3(float a) { return mk3(a, a, a); }
@@ -44,7 +52,7 @@ LFD f3 refract3(f3 I, f3 N, float eta) {
     if (k < 0.0f) return mk3(0.0f);
     return eta * I - (eta * ndi + sqrtf(k)) * N;
 }
-LFD f3 pow3(f3 a, float e) { return mk3(powf(a.x, e), powf(a.y, e), powf(a.z, e)); }
+LFD f3 pow3(f3 a, float e) { return mk3(lf_pow(a.x, e), lf_pow(a.y, e), lf_pow(a.z, e)); }
 
 constexpr float kPI = 3.14159265358979323f;        // globals.glsl:6-9
 constexpr float kTWO_PI = 6.28318530717958648f;
@@ -360,9 +368,10 @@ LFD f3 ImportanceSampleGTR1(float rgh, float r1) {   // sampling.glsl:7-21
     float a = gmax(0.001f, rgh);
     float a2 = a * a;
     float phi = r1 * kTWO_PI;
-    float cosTheta = sqrtf((1.0f - powf(a2, 1.0f - r1)) / (1.0f - a2));
+    float cosTheta = sqrtf((1.0f - lf_pow(a2, 1.0f - r1)) / (1.0f - a2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    float sinPhi, cosPhi;
+    lf_sincos(phi, sinPhi, cosPhi);
     return mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
 }
 LFD f3 ImportanceSampleGTR2(float rgh, float r1, float r2) {   // sampling.glsl:37-49
@@ -370,7 +379,8 @@ LFD f3 ImportanceSampleGTR2(float rgh, float r1, float r2) {   // sampling.glsl:
     float phi = r1 * kTWO_PI;
     float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    float sinPhi, cosPhi;
+    lf_sincos(phi, sinPhi, cosPhi);
     return mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
 }
 LFD float SchlickFresnel(float u) {   // sampling.glsl:52-58
@@ -390,7 +400,7 @@ LFD float GTR1(float NDotH, float a) {   // sampling.glsl:79-87
     if (a >= 1.0f) return (1.0f / kPI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (kPI * logf(a2) * t);
+    return (a2 - 1.0f) / (kPI * lf_log(a2) * t);
 }
 LFD float GTR2(float NDotH, float a) {   // sampling.glsl:90-96
     float a2 = a * a;
@@ -406,8 +416,10 @@ LFD f3 CosineSampleHemisphere(float r1, float r2) {   // sampling.glsl:129-140
     f3 dir;
     float r = sqrtf(r1);
     float phi = kTWO_PI * r2;
-    dir.x = r * cosf(phi);
-    dir.y = r * sinf(phi);
+    float sp, cp;
+    lf_sincos(phi, sp, cp);
+    dir.x = r * cp;
+    dir.y = r * sp;
     dir.z = sqrtf(gmax(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
     return dir;
 }
@@ -415,7 +427,9 @@ LFD f3 UniformSampleSphere(float r1, float r2) {   // sampling.glsl:153-160
     float z = 1.0f - 2.0f * r1;
     float r = sqrtf(gmax(0.0f, 1.0f - z * z));
     float phi = kTWO_PI * r2;
-    return mk3(r * cosf(phi), r * sinf(phi), z);
+    float sp, cp;
+    lf_sincos(phi, sp, cp);
+    return mk3(r * cp, r * sp, z);
 }
 LFD float powerHeuristic(float a, float b) {   // sampling.glsl:163-169
     float t = a * a;
@@ -455,7 +469,7 @@ LFD void sampleOneLight(const LightRec& light, int numLights, f3 surfacePos, Rng
 LFD int wrapi(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
 LFD int wrapn(int i, int n) { i += (i < 0) ? n : 0; i -= (i >= n) ? n : 0; return i; }
 LFD int nearestIdx(float u, int n) { return wrapn((int)floorf(u * (float)n), n); }
-LFD f3 hdrLinear(const DevScene& S, float u, float v) {
+LFN f3 hdrLinear(const DevScene& S, float u, float v) {
     float x = u * (float)S.hdr_w - 0.5f, y = v * (float)S.hdr_h - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float wx = x - fx, wy = y - fy;
@@ -469,14 +483,16 @@ LFD float2 marginalAt(const DevScene& S, float u) { return __ldg(S.marginal + ne
 LFD float2 conditionalAt(const DevScene& S, float u, float v) {
     return __ldg(S.conditional + ((size_t)nearestIdx(v, S.hdr_h) * S.hdr_w + nearestIdx(u, S.hdr_w)));
 }
-LFD float EnvPdf(const DevScene& S, const DevParams& P, f3 dir) {   // sampling.glsl:236-243
-    float theta = acosf(clampf(dir.y, -1.0f, 1.0f));
-    float ux = (kPI + atan2f(dir.z, dir.x)) * (1.0f / kTWO_PI), uy = theta * (1.0f / kPI);
+LFN float EnvPdf(const DevScene& S, const DevParams& P, f3 dir) {   // sampling.glsl:236-243
+    float theta = lf_acos(clampf(dir.y, -1.0f, 1.0f));
+    float ux = (kPI + lf_atan2(dir.z, dir.x)) * (1.0f / kTWO_PI), uy = theta * (1.0f / kPI);
     float pdf = conditionalAt(S, ux, uy).y * marginalAt(S, uy).y;
-    return (pdf * P.hdr_resolution) / (2.0f * kPI * kPI * sinf(theta));
+    float st, ct;
+    lf_sincos(theta, st, ct);
+    return (pdf * P.hdr_resolution) / (2.0f * kPI * kPI * st);
 }
 // sampling.glsl:246-265; returns direction, pdf in .w
-LFD float4 EnvSample(const DevScene& S, const DevParams& P, Rng& rng, f3& color) {
+LFN float4 EnvSample(const DevScene& S, const DevParams& P, Rng& rng, f3& color) {
     float r1 = rnd(rng), r2 = rnd(rng);
     float v = marginalAt(S, r1).x;
     float u = conditionalAt(S, r2, v).x;
@@ -484,14 +500,16 @@ LFD float4 EnvSample(const DevScene& S, const DevParams& P, Rng& rng, f3& color)
     float pdf = conditionalAt(S, u, v).y * marginalAt(S, v).y;
     float phi = u * kTWO_PI;
     float theta = v * kPI;
-    float st = sinf(theta);
+    float st, ct, sph, cph;
+    lf_sincos(theta, st, ct);
+    lf_sincos(phi, sph, cph);
     if (st == 0.0f) pdf = 0.0f;
-    return make_float4(-st * cosf(phi), cosf(theta), -st * sinf(phi), (pdf * P.hdr_resolution) / (2.0f * kPI * kPI * st));
+    return make_float4(-st * cph, ct, -st * sph, (pdf * P.hdr_resolution) / (2.0f * kPI * kPI * st));
 }
 
 // material texture array: RGBA8, LINEAR, REPEAT; fetched unfiltered and lerped in fp32 (Renderer.cpp:151-160)
 template <bool COUNT>
-LFD float4 texArrayLinear(const DevScene& S, float u, float v, int layer, DevCounters* cnt) {
+LFN float4 texArrayLinear(const DevScene& S, float u, float v, int layer, DevCounters* cnt) {
     layer = max(0, min(layer, S.num_tex - 1));
     bump<COUNT>(cnt, C_TEX);
     float x = u * (float)S.tex_w - 0.5f, y = v * (float)S.tex_h - 0.5f;
@@ -509,7 +527,7 @@ LFD float4 texArrayLinear(const DevScene& S, float u, float v, int layer, DevCou
 }
 
 // ---------------------------------------------------------------------------------------------- disney.glsl
-LFD f3 EvalDielectricReflection(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:19-33
+LFN f3 EvalDielectricReflection(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:19-33
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     float F = DielectricFresnel(dot(V, H), s.eta);
@@ -518,7 +536,7 @@ LFD f3 EvalDielectricReflection(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pd
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return s.mat.albedo * F * D * G;
 }
-LFD f3 EvalDielectricRefraction(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:36-52
+LFN f3 EvalDielectricRefraction(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:36-52
     pdf = 0.0f;
     if (dot(N, L) >= 0.0f) return mk3(0.0f);
     float F = DielectricFresnel(fabsf(dot(V, H)), s.eta);
@@ -528,7 +546,7 @@ LFD f3 EvalDielectricRefraction(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pd
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return s.mat.albedo * (1.0f - F) * D * G * fabsf(dot(V, H)) * fabsf(dot(L, H)) * 4.0f * s.eta * s.eta / (denomSqrt * denomSqrt);
 }
-LFD f3 EvalSpecular(const Surf& s, f3 Cspec0, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:55-69
+LFN f3 EvalSpecular(const Surf& s, f3 Cspec0, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:55-69
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     float D = GTR2(dot(N, H), s.mat.roughness);
@@ -538,7 +556,7 @@ LFD f3 EvalSpecular(const Surf& s, f3 Cspec0, f3 V, f3 N, f3 L, f3 H, float& pdf
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return F * D * G;
 }
-LFD f3 EvalClearcoat(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:72-86
+LFN f3 EvalClearcoat(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:72-86
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     float D = GTR1(dot(N, H), mixf(0.1f, 0.001f, s.mat.clearcoatRoughness));
@@ -548,7 +566,7 @@ LFD f3 EvalClearcoat(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // d
     float G = SmithG_GGX(dot(N, L), 0.25f) * SmithG_GGX(dot(N, V), 0.25f);
     return mk3(0.25f * s.mat.clearcoat * F * D * G);
 }
-LFD f3 EvalDiffuse(const Surf& s, f3 Csheen, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:89-113
+LFN f3 EvalDiffuse(const Surf& s, f3 Csheen, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // disney.glsl:89-113
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     pdf = dot(N, L) * (1.0f / kPI);
@@ -624,7 +642,7 @@ LFD f3 DisneySample(const Surf& s, f3 V, f3 N, Rng& rng, f3& L, float& pdf) {   
     return f;
 }
 
-LFD f3 DisneyEval(const Surf& s, f3 V, f3 N, f3 L, float& pdf) {   // disney.glsl:228-291
+LFN f3 DisneyEval(const Surf& s, f3 V, f3 N, f3 L, float& pdf) {   // disney.glsl:228-291
     f3 H;
     bool refl = dot(N, L) > 0.0f;
     if (refl) H = normalize(L + V);
@@ -756,7 +774,9 @@ LFD Ray camera_ray(const DevParams& P, int lx, int ly, int frame, Rng& rng) {
     f3 focalPoint = P.focal_dist * rayDir;
     float cam_r1 = rnd(rng) * kTWO_PI;
     float cam_r2 = rnd(rng) * P.aperture;
-    f3 randomAperturePos = (cosf(cam_r1) * right + sinf(cam_r1) * up) * sqrtf(cam_r2);
+    float sl, cl;
+    lf_sincos(cam_r1, sl, cl);
+    f3 randomAperturePos = (cl * right + sl * up) * sqrtf(cam_r2);
     f3 finalRayDir = normalize(focalPoint - randomAperturePos);
     Ray r; r.o = pos + randomAperturePos; r.d = finalRayDir;
     return r;

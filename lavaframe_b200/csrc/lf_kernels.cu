@@ -40,7 +40,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
             ps.rad = ps.rad + mk3(P.bg[0], P.bg[1], P.bg[2]) * ps.thr;
         } else if (P.use_envmap) {
             float misWeight = 1.0f;
-            float ux = (kPI + atan2f(rd.z, rd.x)) * (1.0f / kTWO_PI), uy = acosf(rd.y) * (1.0f / kPI);
+            float ux = (kPI + lf_atan2(rd.z, rd.x)) * (1.0f / kTWO_PI), uy = lf_acos(rd.y) * (1.0f / kPI);
             if (depth > 0) {
                 float lightPdf = EnvPdf(S, P, rd);
                 misWeight = powerHeuristic(ps.bsdf_pdf, lightPdf);
@@ -68,7 +68,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
     ps.rad = ps.rad + s.mat.emission * ps.thr;                     // :253
     {
         f3 a = -ps.absn * t;                                      // :264
-        ps.thr = ps.thr * mk3(expf(a.x), expf(a.y), expf(a.z));
+        ps.thr = ps.thr * mk3(lf_exp(a.x), lf_exp(a.y), lf_exp(a.z));
     }
 
     // ---- DirectLight (pathtrace.glsl:126-204): weighted candidates now, visibility later
@@ -120,7 +120,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
     ps.bsdf_pdf = pdf;
     if (dot(s.ffnormal, L) < 0.0f) {
         f3 e = s.mat.extinction;
-        ps.absn = -mk3(logf(e.x), logf(e.y), logf(e.z)) / s.mat.atDistance;
+        ps.absn = -mk3(lf_log(e.x), lf_log(e.y), lf_log(e.z)) / s.mat.atDistance;
     }
     if (pdf > 0.0f) ps.thr = ps.thr * (f * fabsf(dot(s.ffnormal, L)) / pdf);
     else return false;

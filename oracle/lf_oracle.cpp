@@ -4,9 +4,10 @@
 // GLSL built-ins are restated the way Mesa's GLSL front end + llvmpipe evaluate them (the only runnable
 // reference implementation): normalize(v) = v * (1/sqrt(dot(v,v))), min/max with
 // x86 MINPS/MAXPS operand semantics, dot() summed left to right, mat*vec summed column by column,
-// inverse() by cofactors times 1/det.  Transcendentals use libm (llvmpipe uses polynomial approximations;
-// the north_star tolerances absorb the difference).
+// inverse() by cofactors times 1/det.  Transcendentals: lf_math_oracle.h (plain-fp32 Cephes kernels; llvmpipe uses
+// its own polynomial approximations and the north_star tolerances absorb the difference).
 #include "lf_oracle.h"
+#include "lf_math_oracle.h"
 
 #include <cmath>
 #include <cstring>
@@ -58,9 +59,9 @@ static inline vec3 refract(vec3 I, vec3 N, float eta) {
     if (k < 0.0f) return V3(0.0f);
     return eta * I - (eta * ndi + sqrtf(k)) * N;
 }
-static inline vec3 pow3(vec3 a, float e) { return {powf(a.x, e), powf(a.y, e), powf(a.z, e)}; }
-static inline vec3 exp3(vec3 a) { return {expf(a.x), expf(a.y), expf(a.z)}; }
-static inline vec3 log3(vec3 a) { return {logf(a.x), logf(a.y), logf(a.z)}; }
+static inline vec3 pow3(vec3 a, float e) { return {lfom::pow(a.x, e), lfom::pow(a.y, e), lfom::pow(a.z, e)}; }
+static inline vec3 exp3(vec3 a) { return {lfom::exp(a.x), lfom::exp(a.y), lfom::exp(a.z)}; }
+static inline vec3 log3(vec3 a) { return {lfom::log(a.x), lfom::log(a.y), lfom::log(a.z)}; }
 
 struct mat4 { vec4 c[4]; };   // columns
 struct mat3 { vec3 c[3]; };
@@ -474,9 +475,10 @@ static vec3 ImportanceSampleGTR1(float rgh, float r1, float r2) {   // sampling.
     float a = gmax(0.001f, rgh);
     float a2 = a * a;
     float phi = r1 * TWO_PI;
-    float cosTheta = sqrtf((1.0f - powf(a2, 1.0f - r1)) / (1.0f - a2));
+    float cosTheta = sqrtf((1.0f - lfom::pow(a2, 1.0f - r1)) / (1.0f - a2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    float sinPhi, cosPhi;
+    lfom::sincos(phi, sinPhi, cosPhi);
     (void)r2;
     return {sinTheta * cosPhi, sinTheta * sinPhi, cosTheta};
 }
@@ -485,7 +487,8 @@ static vec3 ImportanceSampleGTR2(float rgh, float r1, float r2) {   // sampling.
     float phi = r1 * TWO_PI;
     float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    float sinPhi, cosPhi;
+    lfom::sincos(phi, sinPhi, cosPhi);
     return {sinTheta * cosPhi, sinTheta * sinPhi, cosTheta};
 }
 static float SchlickFresnel(float u) {   // sampling.glsl:52-58
@@ -505,7 +508,7 @@ static float GTR1(float NDotH, float a) {   // sampling.glsl:79-87
     if (a >= 1.0f) return (1.0f / PI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (PI * logf(a2) * t);
+    return (a2 - 1.0f) / (PI * lfom::log(a2) * t);
 }
 static float GTR2(float NDotH, float a) {   // sampling.glsl:90-96
     float a2 = a * a;
@@ -521,8 +524,10 @@ static vec3 CosineSampleHemisphere(float r1, float r2) {   // sampling.glsl:129-
     vec3 dir;
     float r = sqrtf(r1);
     float phi = TWO_PI * r2;
-    dir.x = r * cosf(phi);
-    dir.y = r * sinf(phi);
+    float sp, cp;
+    lfom::sincos(phi, sp, cp);
+    dir.x = r * cp;
+    dir.y = r * sp;
     dir.z = sqrtf(gmax(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
     return dir;
 }
@@ -530,7 +535,9 @@ static vec3 UniformSampleSphere(float r1, float r2) {   // sampling.glsl:153-160
     float z = 1.0f - 2.0f * r1;
     float r = sqrtf(gmax(0.0f, 1.0f - z * z));
     float phi = TWO_PI * r2;
-    return {r * cosf(phi), r * sinf(phi), z};
+    float sp, cp;
+    lfom::sincos(phi, sp, cp);
+    return {r * cp, r * sp, z};
 }
 static float powerHeuristic(float a, float b) {   // sampling.glsl:163-169
     float t = a * a;
@@ -572,10 +579,12 @@ static void sampleOneLight(Inv& g, const Light& light, vec3 surfacePos, LightSam
     else sampleDistantLight(g, light, surfacePos, rec);
 }
 static float EnvPdf(Inv& g, const Ray& r) {   // sampling.glsl:236-243
-    float theta = acosf(clampf(r.direction.y, -1.0f, 1.0f));
-    vec2 uv = {(PI + atan2f(r.direction.z, r.direction.x)) * (1.0f / TWO_PI), theta * (1.0f / PI)};
+    float theta = lfom::acos(clampf(r.direction.y, -1.0f, 1.0f));
+    vec2 uv = {(PI + lfom::atan2(r.direction.z, r.direction.x)) * (1.0f / TWO_PI), theta * (1.0f / PI)};
     float pdf = conditional(g.o, uv.x, uv.y).y * marginal(g.o, uv.y).y;
-    return (pdf * (float)(g.o->scene.hdr_width * g.o->scene.hdr_height)) / (2.0f * PI * PI * sinf(theta));
+    float st, ct;
+    lfom::sincos(theta, st, ct);
+    return (pdf * (float)(g.o->scene.hdr_width * g.o->scene.hdr_height)) / (2.0f * PI * PI * st);
 }
 static vec4 EnvSample(Inv& g, vec3& color) {   // sampling.glsl:246-265
     float r1 = rnd(g), r2 = rnd(g);
@@ -586,9 +595,12 @@ static vec4 EnvSample(Inv& g, vec3& color) {   // sampling.glsl:246-265
     float pdf = conditional(g.o, u, v).y * marginal(g.o, v).y;
     float phi = u * TWO_PI;
     float theta = v * PI;
-    if (sinf(theta) == 0.0f) pdf = 0.0f;
+    float st, ct, sph, cph;
+    lfom::sincos(theta, st, ct);
+    lfom::sincos(phi, sph, cph);
+    if (st == 0.0f) pdf = 0.0f;
     float hdrResolution = (float)(g.o->scene.hdr_width * g.o->scene.hdr_height);
-    return {-sinf(theta) * cosf(phi), cosf(theta), -sinf(theta) * sinf(phi), (pdf * hdrResolution) / (2.0f * PI * PI * sinf(theta))};
+    return {-st * cph, ct, -st * sph, (pdf * hdrResolution) / (2.0f * PI * PI * st)};
 }
 static vec3 EmitterSample(const State& state, const LightSampleRec& lrec, const BsdfSampleRec& brec) {   // sampling.glsl:271-282
     if (state.depth == 0) return lrec.emission;
@@ -878,7 +890,7 @@ static vec3 PathTrace(Inv& g, Ray r) {   // pathtrace.glsl:208-295
                 radiance += vec3{o->params.bg_color[0], o->params.bg_color[1], o->params.bg_color[2]} * throughput;
             } else if (o->params.use_envmap) {
                 float misWeight = 1.0f;
-                vec2 uv = {(PI + atan2f(r.direction.z, r.direction.x)) * (1.0f / TWO_PI), acosf(r.direction.y) * (1.0f / PI)};
+                vec2 uv = {(PI + lfom::atan2(r.direction.z, r.direction.x)) * (1.0f / TWO_PI), lfom::acos(r.direction.y) * (1.0f / PI)};
                 if (depth > 0) {
                     float lightPdf = EnvPdf(g, r);
                     misWeight = powerHeuristic(bsdfSampleRec.pdf, lightPdf);
@@ -976,7 +988,9 @@ static Ray CameraRay(Inv& g, int lx, int ly, int tileX, int tileY, int frame, in
     vec3 focalPoint = C.focal_dist * rayDir;
     float cam_r1 = rnd(g) * TWO_PI;
     float cam_r2 = rnd(g) * C.aperture;
-    vec3 randomAperturePos = (cosf(cam_r1) * right + sinf(cam_r1) * up) * sqrtf(cam_r2);
+    float sl, cl;
+    lfom::sincos(cam_r1, sl, cl);
+    vec3 randomAperturePos = (cl * right + sl * up) * sqrtf(cam_r2);
     vec3 finalRayDir = normalize(focalPoint - randomAperturePos);
     return {pos + randomAperturePos, finalRayDir};
 }

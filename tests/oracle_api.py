@@ -22,7 +22,7 @@ def load_oracle():
         return _lib
     path = os.path.join(ORACLE_DIR, "liblforacle.so")
     src_newer = any(os.path.getmtime(os.path.join(ORACLE_DIR, f)) > os.path.getmtime(path)
-                    for f in ("lf_oracle.cpp", "lf_oracle.h", "lf_oracle_capi.cpp")) if os.path.exists(path) else True
+                    for f in ("lf_oracle.cpp", "lf_oracle.h", "lf_math_oracle.h", "lf_oracle_capi.cpp")) if os.path.exists(path) else True
     if src_newer:
         build_oracle()
     lib = C.CDLL(path)

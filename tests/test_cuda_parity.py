@@ -62,24 +62,25 @@ def test_primary_hits_vs_llvmpipe(tracer, golden_dir, name):
 @pytest.mark.parametrize("name", SCENES)
 @pytest.mark.parametrize("mode", [0, 1])
 def test_radiance_vs_oracle(tracer, golden_dir, oracle_lib, name, mode):
-    """Check 2, CUDA vs oracle, wavefront (mode 0) and megakernel (mode 1): 1-spp radiance of frame 2 and a 4-frame sum."""
+    """Check 2, CUDA vs oracle, wavefront (mode 0) and megakernel (mode 1): 1-spp radiance of frame 2 and an 8-frame sum
+    must be IDENTICAL BIT FOR BIT on every pixel - diffuse, glass, rough metal, clearcoat, textures, env map alike.
+    Both sides evaluate the same fp32 expression trees without FMA contraction and the same plain-fp32 transcendental
+    kernels (lf_math.cuh / lf_math_oracle.h), so there is no tolerance to hide a bug in."""
     pack = lf.ScenePack(pack_path(golden_dir, name))
     tracer.upload_pack(pack, kernel_mode=mode)
     o = Oracle(pack.path)
-    for first, n in ((2, 1), (3, 4)):
+    for first, n in ((2, 1), (3, 8)):
         tracer.clear()
         tracer.render_frames(first, n)
         img = tracer.read_accum()
         ref = o.render_frames(first, n)
-        frac = radiance_agreement(img, ref)
-        exact = float(np.mean(np.all(img == ref, axis=2)))
-        assert frac >= MIN_VS_ORACLE[name], f"{name} mode {mode} frames {first}+{n}: within 1e-3 on {frac:.6f} (bit-exact on {exact:.6f})"
+        differ = int((img != ref).any(axis=2).sum())
+        assert differ == 0, f"{name} mode {mode} frames {first}+{n}: {differ} pixels differ (within 1e-3 on {radiance_agreement(img, ref):.6f})"
     o.close()
 
 
-# CUDA vs oracle: same operation order, no FMA; the only differences are last-ulp results of sinf/cosf/powf/expf/logf/
-# acosf/atan2f between CUDA's and glibc's libm, which glass/metal chains amplify (see tests/test_oracle_golden.py).
-MIN_VS_ORACLE = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.98}
+# CUDA vs the reference on llvmpipe: bounded by how well ANY implementation can match llvmpipe (tests/test_oracle_golden.py)
+MIN_VS_LLVMPIPE = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.98}
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -90,7 +91,7 @@ def test_radiance_vs_llvmpipe(tracer, golden_dir, name):
     tracer.clear()
     tracer.render_frames(2, 1)
     frac = radiance_agreement(tracer.read_accum(), g["spp1"])
-    assert frac >= MIN_VS_ORACLE[name], f"{name}: 1-spp within 1e-3 on {frac:.6f}"
+    assert frac >= MIN_VS_LLVMPIPE[name], f"{name}: 1-spp within 1e-3 on {frac:.6f}"
     n = int(g["nspp"])
     tracer.clear()
     tracer.render_frames(2, n)
