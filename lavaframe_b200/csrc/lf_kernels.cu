@@ -205,14 +205,20 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 //     per refill, positions by ballot prefix, so a warp never idles behind its longest ray.
 //   * Shadow work item = path slot with up to two NEE rays (env, analytic light), traced one after the other by the
 //     same lane; radiance += (visible sum) * throughput is applied when the second is done (pathtrace.glsl:266).
-constexpr int kRefillMin = 8;      // idle lanes that trigger a refill from the queue
-constexpr int kLeafGather = 3;     // leaf phase starts when live lanes / kLeafGather are parked at a leaf
+#ifndef LF_REFILL_MIN
+#define LF_REFILL_MIN 8
+#endif
+#ifndef LF_LEAF_GATHER
+#define LF_LEAF_GATHER 3
+#endif
+constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refill from the queue
+constexpr int kLeafGather = LF_LEAF_GATHER;   // leaf phase starts when live lanes / kLeafGather are parked at a leaf
 
 template <bool ANY, bool CULL, bool COUNT, int STACK>
 __global__ void __launch_bounds__(kBlockThreads) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
                                                        int* cursor, DevCounters* cnt) {
     __shared__ int stack[STACK * kBlockThreads];
-    __shared__ float wray[6 * kBlockThreads];           // world-space ray of each lane (restored when a BLAS is left)
+    __shared__ float wray[9 * kBlockThreads];           // world-space ray of each lane + 1/direction (restored when a BLAS is left)
     int* stk = stack + threadIdx.x;
     float* wr = wray + threadIdx.x;
     const int count = *countp;
@@ -240,6 +246,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_trace(DevScene S, PathSoA A, 
         bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
         if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return false;
         walk_begin(S, r, w, stk);
+        wr[6 * kBlockThreads] = w.idir.x; wr[7 * kBlockThreads] = w.idir.y; wr[8 * kBlockThreads] = w.idir.z;
         return true;
     };
     // shadow: load NEE ray `phase` of the slot
@@ -278,23 +285,39 @@ __global__ void __launch_bounds__(kBlockThreads) k_trace(DevScene S, PathSoA A, 
         }
         if (!__any_sync(FULL, alive)) break;
 
-        // ---- phase 1: every lane steps through inner nodes / instance entries; a lane that reaches a triangle leaf
-        // parks there.  The phase ends when a third of the live lanes are parked (or nobody can step): leaves are then
-        // tested by many lanes at once, while the walk itself never waits for the slowest lane.
+        // ---- phase 1: every lane steps through inner nodes; a lane that reaches anything else (triangle leaf, instance
+        // entry, end of a BLAS, end of the walk) parks there.  The phase ends when a third of the live lanes are parked
+        // (or nobody can step): the expensive, rarer steps are then done by many lanes at once, while the inner-node
+        // walk never waits for the slowest lane.
         bool rayDone = false;
         const int liveLanes = __popc(__ballot_sync(FULL, alive));
         for (;;) {
-            const bool atLeaf = alive && !rayDone && w.ref < 0 && !(w.ref & kRefTlasBit);
-            const bool canStep = alive && !rayDone && !atLeaf;
-            const unsigned leafMask = __ballot_sync(FULL, atLeaf), stepMask = __ballot_sync(FULL, canStep);
-            if (stepMask == 0u || __popc(leafMask) * kLeafGather >= liveLanes) break;
+            const bool canStep = alive && w.ref >= 0;
+            const unsigned stepMask = __ballot_sync(FULL, canStep);
+            if (stepMask == 0u || (liveLanes - __popc(stepMask)) * kLeafGather >= liveLanes) break;
             if (canStep) {
-                Ray r;
-                if (w.ref < 0) r = world_ray();              // only instance entries / exits read the world ray
-                if (!walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt)) rayDone = true;
+                Ray r;                                       // not read by an inner-node step
+                walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
             }
         }
-        // ---- phase 2: the parked leaves' triangles, together
+        // ---- phase 2a: instance entries / exits of the parked lanes, together
+        if (alive && w.ref < 0 && (w.ref & kRefTlasBit)) {
+            if (w.ref == kRefSentinel) {
+                if (!w.inBlas) rayDone = true;
+                else {                                       // leave the BLAS: world ray and its reciprocal from shared memory
+                    w.inBlas = false;
+                    Ray r = world_ray();
+                    w.o = r.o; w.d = r.d;
+                    w.idir = mk3(wr[6 * kBlockThreads], wr[7 * kBlockThreads], wr[8 * kBlockThreads]);
+                    w.ref = stk[(--w.sp) * kBlockThreads];
+                }
+            } else {
+                Ray r = world_ray();
+                walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+            }
+        }
+        __syncwarp();
+        // ---- phase 2b: the parked leaves' triangles, together
         if (alive && !rayDone && w.ref < 0 && !(w.ref & kRefTlasBit)) {
             if (walk_leaf<ANY, COUNT>(S, w, maxDist, hit, cnt)) { rayDone = true; hit.light = 0; }      // ANY: occluded
             else w.ref = stk[(--w.sp) * kBlockThreads];
