@@ -215,6 +215,7 @@ def main():
     import torch.distributed as dist
     import lavaframe_b200 as lf
     from lavaframe_b200.pathtracer import algorithmic_bytes_split, algorithmic_bytes_total
+    from lavaframe_b200.multigpu import rank_frames
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,7 +253,9 @@ def main():
 
     def step_frames(i):
         """first frame / stride of this rank in step i: global frame numbers 2, 3, ... dealt round-robin to the ranks."""
-        return 2 + i * S * world + rank, world
+        f0, n, st = rank_frames(2 + i * S * world, S * world, rank, world)
+        assert n == S
+        return f0, st
 
     def sync():
         torch.cuda.synchronize()
@@ -261,6 +264,8 @@ def main():
     for i in range(Wm):
         f0, st = step_frames(i)
         pt.render_frames(f0, S, st)
+    if world > 1:
+        pt.reduce()                                    # warm-up of the collective too (NCCL connects lazily on first use)
     sync()
 
     # ---- timed region: K steps (+ one NCCL sum), device resident
