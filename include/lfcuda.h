@@ -96,6 +96,17 @@ typedef struct LfParams {
     int32_t frames_in_flight;        /* pixel-sample frames batched per wavefront pass; 0 = auto */
 } LfParams;
 
+/* Uniforms of the post-process pass beyond invSampleCounter / tonemapIndex (shaders/postprocess.glsl:11-24;
+ * TiledRenderer.cpp:539-553; RenderOptions, Renderer.h:35-43).  All zero = plain divide + tonemap. */
+typedef struct LfPostParams {
+    int32_t use_ca;              /* useCA: chromatic aberration (postprocess.glsl:96-118) */
+    int32_t use_ca_distortion;   /* useCADistortion */
+    float   ca_distance;         /* caDistance */
+    float   ca_p1, ca_p2, ca_p3; /* caP1 (angularity), caP2 (directionality), caP3 (centre) */
+    int32_t use_vignette;        /* useVignette (postprocess.glsl:121-124,168-170) */
+    float   vignette_intensity, vignette_power;
+} LfPostParams;
+
 /* uniform Camera camera (shaders/common/globals.glsl:48-58; TiledRenderer.cpp:507-513) */
 typedef struct LfCamera {
     float position[3];
@@ -159,6 +170,7 @@ int  lfcuda_update_instances(lfcuda_ctx* ctx, const float* transforms, int32_t n
 /* ---- per-frame uniforms (TiledRenderer::Init :222-227, ::Update :505-521) ----------------------- */
 int  lfcuda_set_params(lfcuda_ctx* ctx, const LfParams* params);
 int  lfcuda_set_camera(lfcuda_ctx* ctx, const LfCamera* camera);
+int  lfcuda_set_post(lfcuda_ctx* ctx, const LfPostParams* post);   /* NULL = defaults (no CA, no vignette) */
 
 /* ---- the hot path ------------------------------------------------------------------------------- */
 /* glClear of accumFBO (TiledRenderer.cpp:478-480). */
@@ -172,8 +184,8 @@ int  lfcuda_render_frames(lfcuda_ctx* ctx, int32_t first_frame, int32_t nframes,
 /* Copy the accumulation buffer (running SUM, W*H*3 floats, rows bottom-up like glGetTexImage,
  * TiledRenderer.cpp:399-414) to host memory.  Synchronises the stream. */
 int  lfcuda_read_accum(lfcuda_ctx* ctx, float* rgb_out);
-/* accum * (1/sample_count) through tonemap `tonemap_index` of shaders/postprocess.glsl:126-172
- * (0 = identity); rows bottom-up; W*H*3 floats.  This is GetOutputBufferHDR's payload. */
+/* The post-process pass (shaders/postprocess.glsl:126-172): accum * (1/sample_count) [or the chromatic-aberration
+ * fetches], tonemap `tonemap_index` (0 = identity), vignette; rows bottom-up; W*H*3 floats.  GetOutputBufferHDR's payload. */
 int  lfcuda_read_output(lfcuda_ctx* ctx, float inv_sample_counter, int32_t tonemap_index, float* rgb_out);
 /* Same, converted to 8-bit like glGetTexImage(GL_RGB, GL_UNSIGNED_BYTE) (TiledRenderer.cpp:382-397). */
 int  lfcuda_read_output_u8(lfcuda_ctx* ctx, float inv_sample_counter, int32_t tonemap_index, uint8_t* rgb_out);

@@ -4,11 +4,11 @@ The product is the CUDA library `liblfcuda.so` (C ABI: include/lfcuda.h) plus th
 (`liblfhost.so`), a drop-in for the reference's TiledRenderer.  This Python package is only the ctypes
 glue used by the tests, `bench.py` and `__graft_entry__.py`; there is no Python or CPU compute path.
 """
-from .capi import (LfSceneView, LfParams, LfCamera, LfCounters, LfStageStats, load_lfcuda, load_lfhost, LfCudaError,
+from .capi import (LfSceneView, LfParams, LfCamera, LfPostParams, LfCounters, LfStageStats, load_lfcuda, load_lfhost, LfCudaError,
                    STAGE_NAMES)
 from .scenepack import ScenePack
 from .pathtracer import PathTracer
 from .host import HostScene, CudaRenderer
 
-__all__ = ["LfSceneView", "LfParams", "LfCamera", "LfCounters", "LfStageStats", "load_lfcuda", "load_lfhost",
+__all__ = ["LfSceneView", "LfParams", "LfCamera", "LfPostParams", "LfCounters", "LfStageStats", "load_lfcuda", "load_lfhost",
            "LfCudaError", "STAGE_NAMES", "ScenePack", "PathTracer", "HostScene", "CudaRenderer"]

@@ -41,6 +41,12 @@ class LfCamera(C.Structure):
                 ("fov", C.c_float), ("focal_dist", C.c_float), ("aperture", C.c_float)]
 
 
+class LfPostParams(C.Structure):
+    _fields_ = [("use_ca", C.c_int32), ("use_ca_distortion", C.c_int32), ("ca_distance", C.c_float), ("ca_p1", C.c_float),
+                ("ca_p2", C.c_float), ("ca_p3", C.c_float), ("use_vignette", C.c_int32), ("vignette_intensity", C.c_float),
+                ("vignette_power", C.c_float)]
+
+
 class LfCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "rays_closest", "rays_shadow", "inner_visits", "leaf_visits", "tri_tests",
                                           "tlas_visits", "light_tests", "shaded_hits", "env_nee", "env_miss", "tex_samples",
@@ -77,6 +83,7 @@ LFCUDA_SYMBOLS = {
     "lfcuda_update_instances": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32]),
     "lfcuda_set_params": (C.c_int, [C.c_void_p, C.POINTER(LfParams)]),
     "lfcuda_set_camera": (C.c_int, [C.c_void_p, C.POINTER(LfCamera)]),
+    "lfcuda_set_post": (C.c_int, [C.c_void_p, C.POINTER(LfPostParams)]),
     "lfcuda_clear": (C.c_int, [C.c_void_p]),
     "lfcuda_render_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "lfcuda_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -464,7 +464,7 @@ __global__ void k_export_hits(DevScene S, DevParams P, PathSoA A, float* t, int*
     }
 }
 
-// postprocess.glsl:26-172 without chromatic aberration / vignette: color = accum * invSampleCounter, then tonemap.
+// postprocess.glsl:26-172: color = accum * invSampleCounter (or the chromatic-aberration fetches), tonemap, vignette.
 LFD float tm_aces(float c) { return clampf((c * (2.51f * c + 0.03f)) / (c * (2.43f * c + 0.59f) + 0.14f), 0.0f, 1.0f); }
 LFD float tm_kanjero(float c, bool rgb) {
     float v = powf((c * (c * (1.2295f * c + 0.3135f) + 1.1935f * 0.4655f) / (c * (1.1935f * c + 0.4655f) + 0.073f)), 1.7f);
@@ -477,9 +477,32 @@ LFD float tm_uncharted(float c) {
     const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
     return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
 }
-__global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned char* out_u8, int n, float inv, int tonemap) {
+// accumTexture is LINEAR / MIRRORED_REPEAT (TiledRenderer.cpp:165-173): bilinear fetch at a normalised coordinate
+LFD int mirrori(int i, int n) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+LFD float accum_linear(const float* __restrict__ accum, int W, int H, float u, float v, int ch) {
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float wx = x - fx, wy = y - fy;
+    int x0 = mirrori((int)fx, W), x1 = mirrori((int)fx + 1, W), y0 = mirrori((int)fy, H), y1 = mirrori((int)fy + 1, H);
+    float a = accum[3 * ((size_t)y0 * W + x0) + ch], b = accum[3 * ((size_t)y0 * W + x1) + ch];
+    float c = accum[3 * ((size_t)y1 * W + x0) + ch], e = accum[3 * ((size_t)y1 * W + x1) + ch];
+    float top = a + (b - a) * wx, bot = c + (e - c) * wx;
+    return top + (bot - top) * wy;
+}
+__global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned char* out_u8, int W, int H, float inv, int tonemap, LfPostParams pp) {
+    const int n = W * H;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int px = i % W, py = i / W;
+        const float tu = ((float)px + 0.5f) / (float)W, tv = ((float)py + 0.5f) / (float)H;   // TexCoords of the fullscreen quad
         float c[3] = {accum[3 * i] * inv, accum[3 * i + 1] * inv, accum[3 * i + 2] * inv};
+        if (pp.use_ca) {   // chromaticAberration(), postprocess.glsl:96-118: red and blue fetched at +/- an offset
+            float offset = pp.ca_distance;
+            float dx = tu - pp.ca_p3, dy = tv - pp.ca_p3;
+            float dist = 0.f + (powf(sqrtf(dx * dx + dy * dy), pp.ca_p1) * pp.ca_p2);
+            float o = pp.use_ca_distortion ? offset * dist : (offset * 0.025f) * pp.ca_p2;
+            c[0] = accum_linear(accum, W, H, tu + o, tv + o, 0) * inv;
+            c[2] = accum_linear(accum, W, H, tu - o, tv - o, 2) * inv;
+        }
         const float g = 1.0f / 2.2f;
         if (tonemap == 1) {
             float lum = 0.3f * c[0] + 0.6f * c[1] + 0.1f * c[2];
@@ -494,6 +517,11 @@ __global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned c
             for (int k = 0; k < 3; k++) c[k] = tm_hejl(c[k]);
         } else if (tonemap == 6) {
             for (int k = 0; k < 3; k++) c[k] = powf(tm_uncharted(c[k]), g) * 1.75f;
+        }
+        if (pp.use_vignette) {   // vignette(), postprocess.glsl:121-124
+            float dx = tu - 0.5f, dy = tv - 0.5f;
+            float d = 1.0f - powf(sqrtf(dx * dx + dy * dy), pp.vignette_power) * pp.vignette_intensity;
+            for (int k = 0; k < 3; k++) c[k] *= d;
         }
         if (out_f) { out_f[3 * i] = c[0]; out_f[3 * i + 1] = c[1]; out_f[3 * i + 2] = c[2]; }
         if (out_u8)
@@ -578,8 +606,8 @@ void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* e
     int n = L.params.tile_w * L.params.tile_h;
     k_export_hits<<<(n + 255) / 256, 256, 0, L.stream>>>(L.scene, L.params, L.soa, t, tri, mat, emitter);
 }
-void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int npix, float inv, int tonemap) {
-    k_post<<<(npix + 255) / 256, 256, 0, stream>>>(accum, out_f, out_u8, npix, inv, tonemap);
+void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int W, int H, float inv, int tonemap, const LfPostParams& pp) {
+    k_post<<<(W * H + 255) / 256, 256, 0, stream>>>(accum, out_f, out_u8, W, H, inv, tonemap, pp);
 }
 
 }  // namespace lf

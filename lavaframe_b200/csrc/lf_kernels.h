@@ -26,6 +26,6 @@ void launch_accumulate(const LaunchCtx& L, float* accum);
 void launch_megakernel(const LaunchCtx& L);
 void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* emitter);
 void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int passes, float* sink, int blocks);
-void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int npix, float inv, int tonemap);
+void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int W, int H, float inv, int tonemap, const LfPostParams& pp);
 
 }  // namespace lf

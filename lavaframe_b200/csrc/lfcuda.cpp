@@ -60,6 +60,7 @@ struct lfcuda_ctx {
     bool have_params = false, have_camera = false;
     LfParams params{};
     LfCamera camera{};
+    LfPostParams post{};
 
     // path state
     size_t capacity = 0;                  // slots
@@ -451,6 +452,12 @@ int lfcuda_set_camera(lfcuda_ctx* ctx, const LfCamera* c) {
     return 0;
 }
 
+int lfcuda_set_post(lfcuda_ctx* ctx, const LfPostParams* p) {
+    if (!ctx) return LFCUDA_EINVAL;
+    if (p) ctx->post = *p; else ctx->post = LfPostParams{};
+    return 0;
+}
+
 int lfcuda_clear(lfcuda_ctx* ctx) {
     if (!ctx || !ctx->have_params) return fail(ctx, LFCUDA_EINVAL, "render parameters not set");
     CK(cudaSetDevice(ctx->device));
@@ -484,7 +491,7 @@ int lfcuda_read_output(lfcuda_ctx* ctx, float inv_sample_counter, int32_t tonema
     if (!ctx || !ctx->have_params || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "render parameters not set or NULL output");
     CK(cudaSetDevice(ctx->device));
     ctx->launches++;
-    launch_post(ctx->stream, ctx->d_accum, ctx->d_out_f, nullptr, ctx->params.width * ctx->params.height, inv_sample_counter, tonemap_index);
+    launch_post(ctx->stream, ctx->d_accum, ctx->d_out_f, nullptr, ctx->params.width, ctx->params.height, inv_sample_counter, tonemap_index, ctx->post);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, ctx->d_out_f, ctx->accum_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -495,7 +502,7 @@ int lfcuda_read_output_u8(lfcuda_ctx* ctx, float inv_sample_counter, int32_t ton
     if (!ctx || !ctx->have_params || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "render parameters not set or NULL output");
     CK(cudaSetDevice(ctx->device));
     ctx->launches++;
-    launch_post(ctx->stream, ctx->d_accum, nullptr, ctx->d_out_u8, ctx->params.width * ctx->params.height, inv_sample_counter, tonemap_index);
+    launch_post(ctx->stream, ctx->d_accum, nullptr, ctx->d_out_u8, ctx->params.width, ctx->params.height, inv_sample_counter, tonemap_index, ctx->post);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, ctx->d_out_u8, ctx->accum_floats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -64,7 +64,12 @@ namespace LavaFrame
         LfCamera cam;
         lfhost::MakeParams(scene, &params);
         lfhost::MakeCamera(scene, &cam);
-        if (lfcuda_set_params(ctx, &params) != 0 || lfcuda_set_camera(ctx, &cam) != 0)
+        const RenderOptions& ro = scene->renderOptions;      // postShader uniforms, TiledRenderer.cpp:539-553
+        LfPostParams post;
+        post.use_ca = ro.useCA ? 1 : 0; post.use_ca_distortion = ro.useCADistortion ? 1 : 0;
+        post.ca_distance = ro.caDistance; post.ca_p1 = ro.caP1; post.ca_p2 = ro.caP2; post.ca_p3 = ro.caP3;
+        post.use_vignette = ro.useVignette ? 1 : 0; post.vignette_intensity = ro.vignetteIntensity; post.vignette_power = ro.vignettePower;
+        if (lfcuda_set_params(ctx, &params) != 0 || lfcuda_set_camera(ctx, &cam) != 0 || lfcuda_set_post(ctx, &post) != 0)
             printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
     }
 

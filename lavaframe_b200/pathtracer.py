@@ -68,6 +68,9 @@ class PathTracer:
         self._ck(self.lib.lfcuda_set_camera(self.h, C.byref(c)), "lfcuda_set_camera")
         self.camera = c
 
+    def set_post(self, post=None):
+        self._ck(self.lib.lfcuda_set_post(self.h, C.byref(post) if post is not None else None), "lfcuda_set_post")
+
     def set_stream(self, cuda_stream_handle):
         self._ck(self.lib.lfcuda_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)), "lfcuda_set_stream")
 

@@ -207,6 +207,60 @@ def test_postprocess_and_u8(tracer, golden_dir):
     np.testing.assert_allclose(aces, ref, rtol=2e-5, atol=2e-6)
 
 
+def _post_reference(acc, inv, tonemap, pp):
+    """numpy restatement of shaders/postprocess.glsl:96-172 (float64) for the checks below."""
+    H, W, _ = acc.shape
+    a = acc.astype(np.float64)
+    ys, xs = np.mgrid[0:H, 0:W]
+    tu, tv = (xs + 0.5) / W, (ys + 0.5) / H
+
+    def mirror(i, n):
+        m = np.mod(i, 2 * n)
+        return np.where(m < n, m, 2 * n - 1 - m)
+
+    def linear(u, v, ch):
+        x, y = u * W - 0.5, v * H - 0.5
+        fx, fy = np.floor(x), np.floor(y)
+        wx, wy = x - fx, y - fy
+        x0, x1 = mirror(fx.astype(int), W), mirror(fx.astype(int) + 1, W)
+        y0, y1 = mirror(fy.astype(int), H), mirror(fy.astype(int) + 1, H)
+        top = a[y0, x0, ch] + (a[y0, x1, ch] - a[y0, x0, ch]) * wx
+        bot = a[y1, x0, ch] + (a[y1, x1, ch] - a[y1, x0, ch]) * wx
+        return top + (bot - top) * wy
+
+    c = a * inv
+    if pp.use_ca:
+        dist = np.hypot(tu - pp.ca_p3, tv - pp.ca_p3) ** pp.ca_p1 * pp.ca_p2
+        o = pp.ca_distance * dist if pp.use_ca_distortion else pp.ca_distance * 0.025 * pp.ca_p2
+        c[..., 0] = linear(tu + o, tv + o, 0) * inv
+        c[..., 2] = linear(tu - o, tv - o, 2) * inv
+    if tonemap == 2:
+        c = np.clip((c * (2.51 * c + 0.03)) / (c * (2.43 * c + 0.59) + 0.14), 0, 1) ** (1 / 2.2)
+    elif tonemap == 3:
+        c = np.clip(c / (c + 1), 0, 1) ** (1 / 2.2)
+    if pp.use_vignette:
+        c = c * (1.0 - np.hypot(tu - 0.5, tv - 0.5) ** pp.vignette_power * pp.vignette_intensity)[..., None]
+    return c
+
+
+def test_postprocess_ca_and_vignette(tracer, golden_dir):
+    """chromatic aberration (both modes) and vignette of postprocess.glsl."""
+    pack = lf.ScenePack(pack_path(golden_dir, "cornell"))
+    tracer.upload_pack(pack)
+    tracer.clear(); tracer.render_frames(2, 4)
+    acc = tracer.read_accum()
+    for use_dist, tonemap in ((0, 0), (1, 2), (0, 3)):
+        pp = lf.LfPostParams()
+        pp.use_ca, pp.use_ca_distortion, pp.ca_distance, pp.ca_p1, pp.ca_p2, pp.ca_p3 = 1, use_dist, 0.05, 5.0, -0.5, 0.5
+        pp.use_vignette, pp.vignette_intensity, pp.vignette_power = 1, 0.8, 1.5
+        tracer.set_post(pp)
+        out = tracer.read_output(0.25, tonemap)
+        ref = _post_reference(acc, 0.25, tonemap, pp)
+        np.testing.assert_allclose(out, ref, rtol=2e-4, atol=1e-3)   # fp32 vs float64 restatement; pow(x, 1/2.2) is steep at 0
+    tracer.set_post(None)
+    np.testing.assert_array_equal(tracer.read_output(0.25, 0), acc * np.float32(0.25))
+
+
 def test_errors_are_reported(gpu):
     pt = lf.PathTracer(gpu)
     with pytest.raises(lf.LfCudaError, match="no scene"):
