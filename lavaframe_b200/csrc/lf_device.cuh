@@ -682,7 +682,7 @@ LFD void Onb(f3 N, f3& T, f3& B) {   // pathtrace.glsl:7-13
 }
 
 // GetNormalsAndTexCoord + GetMaterialsAndTextures (pathtrace.glsl:16-123) for a surface hit.
-template <bool COUNT>
+template <bool COUNT, bool TEX = true>
 LFD void load_surface(const DevScene& S, const Hit& hit, f3 rdir, Surf& s, DevCounters* cnt) {
     const float4* np = S.trinrm + (size_t)3 * hit.tri;
     const float4* tp = S.tris + (size_t)kTriStride * hit.tri;
@@ -714,7 +714,7 @@ LFD void load_surface(const DevScene& S, const Hit& hit, f3 rdir, Surf& s, DevCo
     mat.extinction = mk3(p6.x, p6.y, p6.z);
     mat.texA = p7.x; mat.texMR = p7.y; mat.texN = p7.z; mat.texE = p7.w;
 
-    if (S.num_tex > 0) {
+    if (TEX && S.num_tex > 0) {
         float tvx = tcx, tvy = 1.0f - tcy;
         if ((int)mat.texA >= 0) {
             float4 c = texArrayLinear<COUNT>(S, tvx, tvy, (int)mat.texA, cnt);

@@ -29,7 +29,9 @@ struct Nee {
 
 // One iteration of the bounce loop after ClosestHit (pathtrace.glsl:223-291).  Returns true when the path
 // continues with ps.ray; NEE candidates (already weighted, visibility pending) go to `nee`.
-template <bool COUNT>
+// ENV / LIGHTS / TEX mirror the reference's shader variants (#define ENVMAP, LIGHTS; a bound texture array): a scene
+// without an env map, analytic lights or textures runs a kernel that does not contain that code at all.
+template <bool COUNT, bool ENV = true, bool LIGHTS = true, bool TEX = true>
 LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs& ps, const Hit& hit, Nee& nee, DevCounters* cnt) {
     nee.has0 = nee.has1 = false;
     const float t = hit.t;
@@ -38,7 +40,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
     if (t == kINF) {   // pathtrace.glsl:223-244
         if (P.use_constant_bg) {
             ps.rad = ps.rad + mk3(P.bg[0], P.bg[1], P.bg[2]) * ps.thr;
-        } else if (P.use_envmap) {
+        } else if (ENV && P.use_envmap) {
             float misWeight = 1.0f;
             float ux = (kPI + lf_atan2(rd.z, rd.x)) * (1.0f / kTWO_PI), uy = lf_acos(rd.y) * (1.0f / kPI);
             if (depth > 0) {
@@ -51,7 +53,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
         return false;
     }
 
-    if (hit.light >= 0) {   // analytic light is the nearest hit (pathtrace.glsl:246-261 with the stale State)
+    if (LIGHTS && hit.light >= 0) {   // analytic light is the nearest hit (pathtrace.glsl:246-261 with the stale State)
         ps.rad = ps.rad + ps.stale * ps.thr;
         LightRec L = load_light(S, hit.light);
         f3 Le = L.emission;
@@ -61,7 +63,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
     }
 
     Surf s;
-    load_surface<COUNT>(S, hit, rd, s, cnt);
+    load_surface<COUNT, TEX>(S, hit, rd, s, cnt);
     ps.stale = s.mat.emission;
 
     if (dot(s.normal, s.ffnormal) > 0.0f) ps.absn = mk3(0.0f);   // :250-251
@@ -76,7 +78,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
     f3 surfacePos = hit.fhp + s.normal * kEPS;
     nee.origin = surfacePos;
     nee.T = ps.thr;
-    if (P.use_envmap && !P.use_constant_bg) {
+    if (ENV && P.use_envmap && !P.use_constant_bg) {
         f3 color;
         bump<COUNT>(cnt, C_ENV_NEE);
         float4 dirPdf = EnvSample(S, P, ps.rng, color);
@@ -94,7 +96,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
             }
         }
     }
-    if (S.num_lights > 0) {
+    if (LIGHTS && S.num_lights > 0) {
         int index = (int)(rnd(ps.rng) * (float)S.num_lights);
         LightRec light = load_light(S, index);
         LightSample ls;
@@ -205,6 +207,9 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 //     per refill, positions by ballot prefix, so a warp never idles behind its longest ray.
 //   * Shadow work item = path slot with up to two NEE rays (env, analytic light), traced one after the other by the
 //     same lane; radiance += (visible sum) * throughput is applied when the second is done (pathtrace.glsl:266).
+#ifndef LF_TRACE_MINBLOCKS
+#define LF_TRACE_MINBLOCKS 8
+#endif
 #ifndef LF_REFILL_MIN
 #define LF_REFILL_MIN 8
 #endif
@@ -215,7 +220,7 @@ constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refil
 constexpr int kLeafGather = LF_LEAF_GATHER;   // leaf phase starts when live lanes / kLeafGather are parked at a leaf
 
 template <bool ANY, bool CULL, bool COUNT, int STACK>
-__global__ void __launch_bounds__(kBlockThreads) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
+__global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
                                                        int* cursor, DevCounters* cnt) {
     __shared__ int stack[STACK * kBlockThreads];
     __shared__ float wray[9 * kBlockThreads];           // world-space ray of each lane + 1/direction (restored when a BLAS is left)
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_trace(DevScene S, PathSoA A, 
 #ifndef LF_SHADE_MINBLOCKS
 #define LF_SHADE_MINBLOCKS 8   // 64 registers: measured best on C2 (4: 137 ms, 8: 113 ms, 10: 123 ms, 12: 128 ms per 8 steps); the kernel is latency-bound
 #endif
-template <bool COUNT>
+template <bool COUNT, bool ENV, bool LIGHTS, bool TEX>
 __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
     const int* queue = Q.active[depth & 1];
     int* next = Q.active[(depth + 1) & 1];
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
             float4 hf = A.hit_f[s]; int4 hi = A.hit_i[s]; float4 hp = A.hit_p[s];
             h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w; h.fhp = xyz(hp);
             Nee nee;
-            alive = shade_bounce<COUNT>(S, P, depth, ps, h, nee, cnt);
+            alive = shade_bounce<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, cnt);
             alive = alive && (depth + 1 < P.max_depth);
             wantShadow = nee.has0 || nee.has1;
             if (wantShadow) {
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_megakernel(DevScene S, DevPar
             Hit h;
             trace<false, CULL, COUNT>(S, ps.ray, 0.f, h, stk, cnt);
             Nee nee;
-            bool go = shade_bounce<COUNT>(S, P, depth, ps, h, nee, cnt);
+            bool go = shade_bounce<COUNT, true, true, true>(S, P, depth, ps, h, nee, cnt);
             if (h.t != kINF && h.light < 0) {
                 f3 Li = mk3(0.0f);
                 Ray sr; sr.o = nee.origin;
@@ -576,10 +581,24 @@ void launch_extend(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;
     launch_trace(L, 0, Q.active[depth & 1], Q.counts + 0 * Q.stride + depth, Q.counts + 2 * Q.stride + depth);
 }
+template <bool ENV, bool LIGHTS, bool TEX>
+static void launch_shade_v(const LaunchCtx& L, int depth, int blocks) {
+    k_shade<false, ENV, LIGHTS, TEX><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+}
 void launch_shade(const LaunchCtx& L, int depth) {
-    int blocks = L.sm_count * 8;
-    if (L.count) k_shade<true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
-    else k_shade<false><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+    int blocks = L.sm_count * LF_SHADE_MINBLOCKS;      // exactly one resident wave (more CTAs than fit measured 25 % slower)
+    if (L.count) { k_shade<true, true, true, true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters); return; }
+    const bool env = L.params.use_envmap != 0, lights = L.scene.num_lights > 0, tex = L.scene.num_tex > 0;
+    switch ((env ? 4 : 0) | (lights ? 2 : 0) | (tex ? 1 : 0)) {
+        case 0: launch_shade_v<false, false, false>(L, depth, blocks); break;
+        case 1: launch_shade_v<false, false, true>(L, depth, blocks); break;
+        case 2: launch_shade_v<false, true, false>(L, depth, blocks); break;
+        case 3: launch_shade_v<false, true, true>(L, depth, blocks); break;
+        case 4: launch_shade_v<true, false, false>(L, depth, blocks); break;
+        case 5: launch_shade_v<true, false, true>(L, depth, blocks); break;
+        case 6: launch_shade_v<true, true, false>(L, depth, blocks); break;
+        default: launch_shade_v<true, true, true>(L, depth, blocks); break;
+    }
 }
 void launch_shadow(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;
