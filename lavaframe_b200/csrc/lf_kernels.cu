@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 //   * Shadow work item = path slot with up to two NEE rays (env, analytic light), traced one after the other by the
 //     same lane; radiance += (visible sum) * throughput is applied when the second is done (pathtrace.glsl:266).
 #ifndef LF_TRACE_MINBLOCKS
-#define LF_TRACE_MINBLOCKS 8
+#define LF_TRACE_MINBLOCKS 9   // 56 registers: 9 CTAs x 128 threads fill the register file (10 -> 48 registers spills, +60 % time)
 #endif
 #ifndef LF_REFILL_MIN
 #define LF_REFILL_MIN 8

@@ -219,7 +219,8 @@ int check_ready(lfcuda_ctx* ctx) {
 void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
     L.scene = c->dev; L.params = D; L.soa = c->soa; L.queues = c->queues; L.counters = c->d_counters; L.stream = c->stream;
     L.sm_count = c->prop.multiProcessorCount;
-    L.persistent_blocks = L.sm_count * c->ctas_per_sm;
+    // the 64-entry stack variant needs 38.4 KB of shared memory per CTA: 5 CTAs per SM are resident, not 9
+    L.persistent_blocks = L.sm_count * (c->packed.stack_depth > 32 ? std::min(c->ctas_per_sm, 5) : c->ctas_per_sm);
     L.stack_depth = c->packed.stack_depth;
     L.cull = !c->params.no_cull;
     L.count = c->params.count_work != 0;

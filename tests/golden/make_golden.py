@@ -10,7 +10,10 @@ and lavaframe_b200/bin/lf_scenepack by CMake):
         spp1                                           1-spp radiance (frame 2), W*H*3 float32, rows bottom-up
         sppN                                           N-spp mean (frames 2..N+1)
 
-Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] ...
+  * cornell_llvmpipe_4096spp.npz   the converged reference image for the north_star's third check (20 min of llvmpipe):
+        spp4096 = mean of frames 2..4097
+
+Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [cornell4096] ...
 """
 import json
 import os
@@ -44,7 +47,19 @@ def run_ref(scene, spp, out, probe=None):
     return json.loads(res.stdout.strip().splitlines()[-1])
 
 
+def converged_cornell(spp=4096):
+    with tempfile.TemporaryDirectory() as tmp:
+        scene = gen_scenes.cornell_256(os.path.join(tmp, "assets"))
+        info = run_ref(scene, spp, os.path.join(tmp, "conv.f32"))
+        img = np.fromfile(os.path.join(tmp, "conv.f32"), np.float32).reshape(info["height"], info["width"], 3)
+        np.savez_compressed(os.path.join(GOLD, f"cornell_llvmpipe_{spp}spp.npz"), **{f"spp{spp}": img, "nspp": np.int32(spp)})
+        print("cornell", spp, "spp mean", img.mean(axis=(0, 1)), "render_s", info["render_s"])
+
+
 def main(names):
+    if "cornell4096" in names:
+        converged_cornell(4096)
+        names = [n for n in names if n != "cornell4096"]
     for name in names:
         builder, nspp = SCENES[name]
         with tempfile.TemporaryDirectory() as tmp:

@@ -99,6 +99,19 @@ def test_radiance_vs_llvmpipe(tracer, golden_dir, name):
     assert rmse_over_mean_luminance(mean, g["sppN"]) < 0.05
 
 
+def test_converged_4096spp_vs_llvmpipe(tracer, golden_dir):
+    """Check 3 of the north_star: the converged 4096-spp Cornell image against the reference's own 4096-spp image
+    (20 minutes of llvmpipe, frames 2..4097): RMSE below 0.5 % of the mean luminance."""
+    g = np.load(os.path.join(golden_dir, "cornell_llvmpipe_4096spp.npz"))
+    tracer.upload_pack(lf.ScenePack(pack_path(golden_dir, "cornell")))
+    tracer.clear()
+    tracer.render_frames(2, 4096)
+    img = tracer.read_output(1.0 / 4096, 0)
+    rel = rmse_over_mean_luminance(img, g["spp4096"])
+    assert rel < 0.005, f"RMSE / mean luminance = {rel:.5f}"
+    assert radiance_agreement(img, g["spp4096"]) >= 0.99
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_wavefront_equals_megakernel(tracer, golden_dir, name):
     """Two kernel organisations of the same device functions must agree bit for bit."""

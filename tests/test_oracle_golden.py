@@ -123,6 +123,20 @@ def test_oracle_vs_llvmpipe(golden_dir, oracle_lib, name):
     o.close()
 
 
+def test_converged_64spp_window_vs_llvmpipe_4096(golden_dir, oracle_lib):
+    """A CPU-sized slice of the converged check: the oracle's 4096-spp mean over a 32x32 window of the Cornell frame
+    against the reference's 4096-spp image (the full-frame check runs on the GPU)."""
+    g = np.load(os.path.join(golden_dir, "cornell_llvmpipe_4096spp.npz"))["spp4096"]
+    o = Oracle(_pack(golden_dir, "cornell"))
+    o.update_params(tile_width=32, tile_height=32)
+    acc = o.render_frames(2, 4096, 1, 3, 4)             # tile (3, 4): pixels x 96..127, y 128..159
+    o.close()
+    win = acc[128:160, 96:128] / np.float32(4096)
+    ref = g[128:160, 96:128]
+    assert rmse_over_mean_luminance(win, ref) < 0.005
+    assert radiance_agreement(win, ref, rel=1e-3) >= 0.99
+
+
 @pytest.mark.parametrize("name", SCENES)
 def test_cull_preserves_results(golden_dir, oracle_lib, name):
     """The distance cull (not in the reference) must not change a single hit or radiance value."""
