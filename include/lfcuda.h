@@ -140,7 +140,7 @@ typedef struct LfCounters {
 /* Device time per wavefront stage, measured with CUDA events on the context's stream while
  * profiling is on (lfcuda_set_profiling). */
 enum { LF_STAGE_GENERATE = 0, LF_STAGE_EXTEND, LF_STAGE_SHADE, LF_STAGE_SHADOW, LF_STAGE_ACCUMULATE,
-       LF_STAGE_MEGAKERNEL, LF_STAGE_COUNT };
+       LF_STAGE_MEGAKERNEL, LF_STAGE_SAMPLE, LF_STAGE_COUNT };
 typedef struct LfStageStats {
     uint64_t launches[LF_STAGE_COUNT];
     double   ms[LF_STAGE_COUNT];

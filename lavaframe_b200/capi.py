@@ -57,11 +57,11 @@ class LfCounters(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
-STAGE_NAMES = ("generate", "extend", "shade", "shadow", "accumulate", "megakernel")
+STAGE_NAMES = ("generate", "extend", "shade", "shadow", "accumulate", "megakernel", "sample")
 
 
 class LfStageStats(C.Structure):
-    _fields_ = [("launches", C.c_uint64 * 6), ("ms", C.c_double * 6)]
+    _fields_ = [("launches", C.c_uint64 * 7), ("ms", C.c_double * 7)]
 
     def as_dict(self):
         return {n: {"launches": int(self.launches[i]), "ms": float(self.ms[i])} for i, n in enumerate(STAGE_NAMES)}

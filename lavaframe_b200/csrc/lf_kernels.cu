@@ -27,12 +27,16 @@ struct Nee {
     bool has0, has1;
 };
 
-// One iteration of the bounce loop after ClosestHit (pathtrace.glsl:223-291).  Returns true when the path
-// continues with ps.ray; NEE candidates (already weighted, visibility pending) go to `nee`.
+// One iteration of the bounce loop after ClosestHit (pathtrace.glsl:223-291), in two parts that the wavefront runs as
+// two kernels (one kernel holding both was instruction-cache and register bound: the two halves cost 0.86 + 0.95 ms
+// apart and 3.07 ms together on C2's first bounce):
+//   shade_hit     :223-266  miss / emitter / surface fetch, emission, absorption, NEE candidates (already weighted,
+//                           visibility pending) -> `nee`; returns true when a surface was hit and `s` is valid
+//   shade_sample  :268-291  DisneySample, throughput, Russian roulette, next ray; returns true when the path continues
 // ENV / LIGHTS / TEX mirror the reference's shader variants (#define ENVMAP, LIGHTS; a bound texture array): a scene
 // without an env map, analytic lights or textures runs a kernel that does not contain that code at all.
 template <bool COUNT, bool ENV = true, bool LIGHTS = true, bool TEX = true>
-LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs& ps, const Hit& hit, Nee& nee, DevCounters* cnt) {
+LFD bool shade_hit(const DevScene& S, const DevParams& P, int depth, PathRegs& ps, const Hit& hit, Nee& nee, Surf& s, f3& absnNext, DevCounters* cnt) {
     nee.has0 = nee.has1 = false;
     const float t = hit.t;
     const f3 rd = ps.ray.d;
@@ -62,7 +66,6 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
         return false;
     }
 
-    Surf s;
     load_surface<COUNT, TEX>(S, hit, rd, s, cnt);
     ps.stale = s.mat.emission;
 
@@ -115,15 +118,21 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
         }
     }
 
-    // ---- BSDF sample (pathtrace.glsl:268-291)
+    {   // the absorption the path takes on if the sampled direction goes below the surface (:271-272)
+        f3 e = s.mat.extinction;
+        absnNext = -mk3(lf_log(e.x), lf_log(e.y), lf_log(e.z)) / s.mat.atDistance;
+    }
+    return true;
+}
+
+// BSDF sample (pathtrace.glsl:268-291).  `s` needs normal, ffnormal, tangent frame, eta and the material.
+LFD bool shade_sample(const DevParams& P, int depth, PathRegs& ps, const Surf& s, f3 fhp, f3 absnNext) {
+    const f3 V = -ps.ray.d;
     f3 L;
     float pdf;
     f3 f = DisneySample(s, V, s.ffnormal, ps.rng, L, pdf);
     ps.bsdf_pdf = pdf;
-    if (dot(s.ffnormal, L) < 0.0f) {
-        f3 e = s.mat.extinction;
-        ps.absn = -mk3(lf_log(e.x), lf_log(e.y), lf_log(e.z)) / s.mat.atDistance;
-    }
+    if (dot(s.ffnormal, L) < 0.0f) ps.absn = absnNext;
     if (pdf > 0.0f) ps.thr = ps.thr * (f * fabsf(dot(s.ffnormal, L)) / pdf);
     else return false;
 
@@ -133,7 +142,7 @@ LFD bool shade_bounce(const DevScene& S, const DevParams& P, int depth, PathRegs
         ps.thr = ps.thr / q;
     }
     ps.ray.d = L;
-    ps.ray.o = hit.fhp + L * kEPS;
+    ps.ray.o = fhp + L * kEPS;
     return true;
 }
 
@@ -360,16 +369,18 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
 #ifndef LF_SHADE_MINBLOCKS
 #define LF_SHADE_MINBLOCKS 8   // 64 registers: measured best on C2 (4: 137 ms, 8: 113 ms, 10: 123 ms, 12: 128 ms per 8 steps); the kernel is latency-bound
 #endif
+// shade, part A: hit processing + next-event estimation.  Surface hits that go on are appended to the sample queue with
+// the part of `State` DisneySample needs (5 float4 per path).
 template <bool COUNT, bool ENV, bool LIGHTS, bool TEX>
 __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
     const int* queue = Q.active[depth & 1];
-    int* next = Q.active[(depth + 1) & 1];
     const int count = Q.counts[0 * Q.stride + depth];
-    int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
+    int* sampleCount = Q.counts + 4 * Q.stride + depth;
     int* shadowCount = Q.counts + 1 * Q.stride + depth;
+    const bool lastBounce = depth + 1 >= P.max_depth;          // the BSDF sample of the last bounce cannot reach the image
     const int rounded = (count + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
-        bool alive = false, wantShadow = false;
+        bool wantSample = false, wantShadow = false;
         int s = -1;
         if (i < count) {
             s = queue[i];
@@ -382,21 +393,76 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
             float4 hf = A.hit_f[s]; int4 hi = A.hit_i[s]; float4 hp = A.hit_p[s];
             h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w; h.fhp = xyz(hp);
             Nee nee;
-            alive = shade_bounce<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, cnt);
-            alive = alive && (depth + 1 < P.max_depth);
+            Surf sf;
+            f3 absnNext;
+            const bool surface = shade_hit<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, sf, absnNext, cnt);
+            wantSample = surface && !lastBounce;
             wantShadow = nee.has0 || nee.has1;
             if (wantShadow) {
                 A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
                 if (nee.has0) { A.sh_d0[s] = make_float4(nee.d0.x, nee.d0.y, nee.d0.z, nee.m0); A.sh_c0[s] = make_float4(nee.c0.x, nee.c0.y, nee.c0.z, 0.f); }
                 if (nee.has1) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
                 A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);
-            } else if (h.t != kINF && h.light < 0) {
+            } else if (surface) {
                 ps.rad = ps.rad + mk3(0.0f) * nee.T;              // radiance += DirectLight() * throughput with Li == 0 (pathtrace.glsl:266)
             }
-            store_state(A, s, ps);
+            // only what part A changed
+            A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
+            A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
+            if (wantSample) {
+                A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
+                A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+                A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+                const Mat& m = sf.mat;
+                A.sf0[s] = make_float4(sf.normal.x, sf.normal.y, sf.normal.z, sf.eta);
+                A.sf1[s] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.specular);
+                A.sf2[s] = make_float4(m.metallic, m.roughness, m.specularTint, m.sheenTint);
+                A.sf3[s] = make_float4(m.sheen, m.clearcoat, m.clearcoatRoughness, m.specTrans);
+                A.sf4[s] = make_float4(absnNext.x, absnNext.y, absnNext.z, m.subsurface);
+            }
+        }
+        queue_push(Q.sample, sampleCount, wantSample, s);
+        queue_push(Q.shadow, shadowCount, wantShadow, s);
+    }
+}
+
+// shade, part B: BSDF sample, throughput, Russian roulette, next ray; survivors are appended to the next bounce's queue.
+__global__ void __launch_bounds__(128, 8) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
+    const int count = Q.counts[4 * Q.stride + depth];
+    int* next = Q.active[(depth + 1) & 1];
+    int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
+    const int rounded = (count + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool alive = false;
+        int s = -1;
+        if (i < count) {
+            s = Q.sample[i];
+            PathRegs ps;
+            float4 d = A.ray_d[s], th = A.thr[s], ab = A.absn[s], hp = A.hit_p[s];
+            float4 f0 = A.sf0[s], f1 = A.sf1[s], f2 = A.sf2[s], f3v = A.sf3[s], f4v = A.sf4[s];
+            uint4 g = A.rng[s];
+            ps.ray.d = xyz(d); ps.ray.o = mk3(0.f); ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.absn = xyz(ab);
+            ps.rad = mk3(0.f); ps.stale = mk3(0.f);
+            ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
+            Surf sf;
+            sf.normal = xyz(f0); sf.eta = f0.w;
+            sf.ffnormal = dot(sf.normal, ps.ray.d) <= 0.0f ? sf.normal : sf.normal * -1.0f;   // pathtrace.glsl:34
+            Onb(sf.normal, sf.tangent, sf.bitangent);                                            // :36
+            Mat& m = sf.mat;
+            m.albedo = xyz(f1); m.specular = f1.w;
+            m.metallic = f2.x; m.roughness = f2.y; m.specularTint = f2.z; m.sheenTint = f2.w;
+            m.sheen = f3v.x; m.clearcoat = f3v.y; m.clearcoatRoughness = f3v.z; m.specTrans = f3v.w;
+            m.subsurface = f4v.w;
+            alive = shade_sample(P, depth, ps, sf, xyz(hp), xyz(f4v));
+            A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
+            if (alive) {
+                A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+                A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
+                A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
+                A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+            }
         }
         queue_push(next, nextCount, alive, s);
-        queue_push(Q.shadow, shadowCount, wantShadow, s);
     }
 }
 
@@ -439,14 +505,17 @@ __global__ void __launch_bounds__(kBlockThreads) k_megakernel(DevScene S, DevPar
             Hit h;
             trace<false, CULL, COUNT>(S, ps.ray, 0.f, h, stk, cnt);
             Nee nee;
-            bool go = shade_bounce<COUNT, true, true, true>(S, P, depth, ps, h, nee, cnt);
-            if (h.t != kINF && h.light < 0) {
+            Surf sf;
+            f3 absnNext;
+            bool go = shade_hit<COUNT, true, true, true>(S, P, depth, ps, h, nee, sf, absnNext, cnt);
+            if (go) {
                 f3 Li = mk3(0.0f);
                 Ray sr; sr.o = nee.origin;
                 Hit dummy;
                 if (nee.has0) { sr.d = nee.d0; if (!trace<true, CULL, COUNT>(S, sr, nee.m0, dummy, stk, cnt)) Li = Li + nee.c0; }
                 if (nee.has1) { sr.d = nee.d1; if (!trace<true, CULL, COUNT>(S, sr, nee.m1, dummy, stk, cnt)) Li = Li + nee.c1; }
                 ps.rad = ps.rad + Li * nee.T;
+                go = shade_sample(P, depth, ps, sf, h.fhp, absnNext);
             }
             if (!go) break;
         }
@@ -599,6 +668,9 @@ void launch_shade(const LaunchCtx& L, int depth) {
         case 6: launch_shade_v<true, true, false>(L, depth, blocks); break;
         default: launch_shade_v<true, true, true>(L, depth, blocks); break;
     }
+}
+void launch_sample(const LaunchCtx& L, int depth) {
+    k_sample<<<L.sm_count * 8, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
 }
 void launch_shadow(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;

@@ -21,6 +21,7 @@ struct LaunchCtx {
 void launch_generate(const LaunchCtx& L);
 void launch_extend(const LaunchCtx& L, int depth);
 void launch_shade(const LaunchCtx& L, int depth);
+void launch_sample(const LaunchCtx& L, int depth);
 void launch_shadow(const LaunchCtx& L, int depth);
 void launch_accumulate(const LaunchCtx& L, float* accum);
 void launch_megakernel(const LaunchCtx& L);

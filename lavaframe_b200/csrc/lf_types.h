@@ -88,6 +88,12 @@ struct PathSoA {
     float4* absn;      // absorption.xyz
     float4* stale;     // state.mat.emission of the last shaded surface (pathtrace.glsl:246-253 on emitter hits)
     uint4*  rng;       // pcg4d state
+    // what DisneySample needs of `State`, handed from the hit/NEE kernel to the sample kernel
+    float4* sf0;       // normal.xyz, eta
+    float4* sf1;       // albedo.xyz, specular
+    float4* sf2;       // metallic, roughness, specularTint, sheenTint
+    float4* sf3;       // sheen, clearcoat, clearcoatRoughness, specTrans
+    float4* sf4;       // -log(extinction)/atDistance .xyz, subsurface
     // next-event estimation requests of the current bounce
     float4* sh_o;      // surfacePos.xyz, number of candidate rays in .w bits
     float4* sh_d0;     // env light direction.xyz, max distance
@@ -100,7 +106,8 @@ struct PathSoA {
 struct Queues {
     int* active[2];    // ping-pong queues of live path slots
     int* shadow;       // slots with at least one shadow ray this bounce
-    int* counts;       // [4][max_depth + 2]: active count, shadow count, extend cursor, shadow cursor per bounce
+    int* sample;       // surface hits that go on to the BSDF-sample kernel
+    int* counts;       // [5][max_depth + 2]: active count, shadow count, extend cursor, shadow cursor, sample count per bounce
     int  stride;       // max_depth + 2
 };
 

@@ -23,6 +23,7 @@ using namespace lf;
 namespace {
 
 thread_local std::string g_create_error;
+constexpr int kCountRows = 5;   // rows of Queues::counts
 
 struct StageEvent { int stage; cudaEvent_t a, b; };
 
@@ -154,7 +155,7 @@ int alloc_state(lfcuda_ctx* ctx) {
         return 0;
     };
     float4** f4s[] = {&ctx->soa.ray_o, &ctx->soa.ray_d, &ctx->soa.hit_f, &ctx->soa.hit_p, &ctx->soa.thr, &ctx->soa.rad, &ctx->soa.absn,
-                      &ctx->soa.stale, &ctx->soa.sh_o, &ctx->soa.sh_d0, &ctx->soa.sh_c0, &ctx->soa.sh_d1, &ctx->soa.sh_c1, &ctx->soa.sh_T};
+                      &ctx->soa.stale, &ctx->soa.sf0, &ctx->soa.sf1, &ctx->soa.sf2, &ctx->soa.sf3, &ctx->soa.sf4, &ctx->soa.sh_o, &ctx->soa.sh_d0, &ctx->soa.sh_c0, &ctx->soa.sh_d1, &ctx->soa.sh_c1, &ctx->soa.sh_T};
     for (float4** p : f4s) { int r = A((void**)p, cap * sizeof(float4)); if (r) return r; }
     int r;
     if ((r = A((void**)&ctx->soa.hit_i, cap * sizeof(int4)))) return r;
@@ -162,8 +163,9 @@ int alloc_state(lfcuda_ctx* ctx) {
     if ((r = A((void**)&ctx->queues.active[0], cap * sizeof(int)))) return r;
     if ((r = A((void**)&ctx->queues.active[1], cap * sizeof(int)))) return r;
     if ((r = A((void**)&ctx->queues.shadow, cap * sizeof(int)))) return r;
+    if ((r = A((void**)&ctx->queues.sample, cap * sizeof(int)))) return r;
     ctx->queues.stride = P.max_depth + 2;
-    if ((r = A((void**)&ctx->queues.counts, (size_t)4 * ctx->queues.stride * sizeof(int)))) return r;
+    if ((r = A((void**)&ctx->queues.counts, (size_t)kCountRows * ctx->queues.stride * sizeof(int)))) return r;
     ctx->accum_floats = (size_t)P.width * P.height * 3;
     if ((r = A((void**)&ctx->d_accum, ctx->accum_floats * sizeof(float)))) return r;
     if ((r = A((void**)&ctx->d_out_f, ctx->accum_floats * sizeof(float)))) return r;
@@ -235,11 +237,12 @@ int run_batch(lfcuda_ctx* ctx, int first_frame, int nframes, int stride, int til
     if (ctx->params.kernel_mode == 1) {
         { StageTimer t(ctx, LF_STAGE_MEGAKERNEL); launch_megakernel(L); }
     } else {
-        CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)4 * ctx->queues.stride * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)kCountRows * ctx->queues.stride * sizeof(int), ctx->stream));
         { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
         for (int d = 0; d < D.max_depth; d++) {
             { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, d); }
             { StageTimer t(ctx, LF_STAGE_SHADE); launch_shade(L, d); }
+            if (d + 1 < D.max_depth) { StageTimer t(ctx, LF_STAGE_SAMPLE); launch_sample(L, d); }
             { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
         }
     }
@@ -538,7 +541,7 @@ int lfcuda_read_primary_hits(lfcuda_ctx* ctx, int32_t frame, float* t_out, int32
     fill_dev_params(ctx, D, frame, 1, 1, 0, 0);
     LaunchCtx L;
     make_launch_ctx(ctx, L, D);
-    CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)4 * ctx->queues.stride * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)kCountRows * ctx->queues.stride * sizeof(int), ctx->stream));
     { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
     { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, 0); }
     ctx->launches++;

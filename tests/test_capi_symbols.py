@@ -33,7 +33,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(lf.LfParams) == 17 * 4
     assert C.sizeof(lf.LfCamera) == 15 * 4
     assert C.sizeof(lf.LfCounters) == 17 * 8
-    assert C.sizeof(lf.LfStageStats) == 6 * 8 + 6 * 8
+    assert C.sizeof(lf.LfStageStats) == 7 * 8 + 7 * 8
     assert C.sizeof(lf.LfSceneView) == 160   # checked against gcc sizeof
 
 
