@@ -370,6 +370,16 @@ def main():
             roofline["frac_of_l2"] = achieved / l2
         except Exception as e:
             roofline["l2_read_gbs_measured"] = f"failed: {e}"
+    # the bound that ncu shows to be the active one (l1tex data-pipe wavefronts): the rate at which this GPU delivers
+    # divergent 64-byte node fetches that hit L2, measured by tools/l1_probe.cu and recorded under profiles/
+    ceil_path = os.path.join(ROOT, "profiles", "l1_fetch_ceiling.json")
+    if os.path.exists(ceil_path):
+        try:
+            ceil = json.load(open(ceil_path))["node_fetch_l2_hit_gbs"]
+            roofline["l1_node_fetch_ceiling_gbs"] = ceil
+            roofline["frac_of_l1_node_fetch_ceiling"] = achieved / ceil
+        except Exception:
+            pass
     mrays = rays * scale * world / (ms * 1e-3) / 1e6
 
     line = {
