@@ -181,6 +181,15 @@ int  lfcuda_clear(lfcuda_ctx* ctx);
  * frame order.  Asynchronous on the context's stream. */
 int  lfcuda_render_frames(lfcuda_ctx* ctx, int32_t first_frame, int32_t nframes, int32_t frame_stride,
                           int32_t tile_x, int32_t tile_y);
+/* The preview engine "Flareon" (shaders/preview_flareon.glsl:22-61), i.e. what TiledRenderer::Render draws instead of the
+ * path-trace pass while camera->isMoving || instancesModified (TiledRenderer.cpp:327-333): one sample per pixel of a
+ * pv_width x pv_height viewport (screenSize * previewScale, :330), RNG frame fixed to 1, uniform maxDepth = max_depth
+ * (2 while moving, :532), thin lens only if use_dof (#define USE_DOF, :90-91).  Written to the preview target, never
+ * accumulated.  Always runs the wavefront kernels.  Asynchronous on the context's stream. */
+int  lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, int32_t max_depth, int32_t use_dof);
+/* The preview target through the post-process pass with invSampleCounter = 1, as Present()/SetViewport() display it
+ * (TiledRenderer.cpp:361-364,558-562): pv_width * pv_height * 3 floats, rows bottom-up.  Synchronises the stream. */
+int  lfcuda_read_preview(lfcuda_ctx* ctx, int32_t tonemap_index, float* rgb_out);
 /* Copy the accumulation buffer (running SUM, W*H*3 floats, rows bottom-up like glGetTexImage,
  * TiledRenderer.cpp:399-414) to host memory.  Synchronises the stream. */
 int  lfcuda_read_accum(lfcuda_ctx* ctx, float* rgb_out);

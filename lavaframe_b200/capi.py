@@ -86,6 +86,8 @@ LFCUDA_SYMBOLS = {
     "lfcuda_set_post": (C.c_int, [C.c_void_p, C.POINTER(LfPostParams)]),
     "lfcuda_clear": (C.c_int, [C.c_void_p]),
     "lfcuda_render_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lfcuda_render_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lfcuda_read_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "lfcuda_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lfcuda_read_output": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
     "lfcuda_read_output_u8": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
@@ -165,5 +167,7 @@ def load_lfhost():
     lib.lfhost_renderer_output_hdr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lfhost_renderer_output_u8.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lfhost_renderer_run.argtypes = [C.c_void_p, C.c_int]
+    lib.lfhost_renderer_preview_hdr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.lfhost_set_preview.argtypes = [C.c_float, C.c_int]
     _lfhost = lib
     return lib

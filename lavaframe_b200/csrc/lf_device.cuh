@@ -782,4 +782,35 @@ LFD Ray camera_ray(const DevParams& P, int lx, int ly, int frame, Rng& rng) {
     return r;
 }
 
+// preview_flareon.glsl:22-61: camera ray of fragment (x, y) of the pv_w x pv_h preview viewport.  RNG seeded with
+// gl_FragCoord.xy and frame 1 (:24); jitter / screenResolution (:33); d = 2 * TexCoords - 1 (:34); the thin lens only
+// under #define USE_DOF (:44-57), its two rand() always drawn (:42-43).
+LFD Ray preview_ray(const DevParams& P, int x, int y, Rng& rng) {
+    float resx = (float)P.width, resy = (float)P.height;
+    float tcx = ((float)x + 0.5f) / (float)P.pv_w, tcy = ((float)y + 0.5f) / (float)P.pv_h;
+    rng.x = (unsigned)x; rng.y = (unsigned)y; rng.z = 1u; rng.w = (unsigned)x + (unsigned)y;   // InitRNG(gl_FragCoord.xy, 1)
+    float r1 = 2.0f * rnd(rng);
+    float r2 = 2.0f * rnd(rng);
+    float jx = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
+    float jy = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
+    jx = jx / resx;
+    jy = jy / resy;
+    float dx = (2.0f * tcx - 1.0f) + jx, dy = (2.0f * tcy - 1.0f) + jy;
+    dy *= resy / resx * P.cam_scale;
+    dx *= P.cam_scale;
+    f3 right = mk3(P.cam_right[0], P.cam_right[1], P.cam_right[2]), up = mk3(P.cam_up[0], P.cam_up[1], P.cam_up[2]);
+    f3 fwd = mk3(P.cam_fwd[0], P.cam_fwd[1], P.cam_fwd[2]), pos = mk3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
+    f3 rayDir = normalize(dx * right + dy * up + fwd);
+    f3 focalPoint = P.focal_dist * rayDir;
+    float cam_r1 = rnd(rng) * kTWO_PI;
+    float cam_r2 = rnd(rng) * P.aperture;
+    Ray r;
+    if (!P.use_dof) { r.o = pos; r.d = normalize(focalPoint); return r; }
+    float sl, cl;
+    lf_sincos(cam_r1, sl, cl);
+    f3 randomAperturePos = (cl * right + sl * up) * sqrtf(cam_r2);
+    r.o = pos + randomAperturePos; r.d = normalize(focalPoint - randomAperturePos);
+    return r;
+}
+
 }  // namespace lf

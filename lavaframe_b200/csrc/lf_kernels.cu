@@ -157,6 +157,15 @@ LFD bool slot_pixel(const DevParams& P, int q, int& lx, int& ly) {
     int px = P.tile_w * P.tile_x + lx, py = P.tile_h * P.tile_y + ly;   // viewport offset of the tile copy (TiledRenderer.cpp:342)
     return px >= 0 && py >= 0 && px < P.width && py < P.height;
 }
+// the same slot order for a band of the preview viewport (no tile offset, no screen clipping)
+LFD bool slot_preview(const DevParams& P, int q, int& lx, int& ly) {
+    int blk = q >> 5, i = q & 31;
+    int bw = P.pix_w8 >> 3;
+    int bx = blk % bw, by = blk / bw;
+    lx = bx * 8 + (i & 7);
+    ly = by * 4 + (i >> 3);
+    return lx < P.pv_w && ly < P.tile_h && P.pv_y0 + ly < P.pv_h;
+}
 LFD int pixel_slot(const DevParams& P, int lx, int ly) {
     int bw = P.pix_w8 >> 3;
     return (((ly >> 2) * bw + (lx >> 3)) << 5) + ((ly & 3) << 3) + (lx & 7);
@@ -192,10 +201,11 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
         int fi = s / P.slots_per_frame, q = s - fi * P.slots_per_frame;
         int lx, ly;
-        bool valid = slot_pixel(P, q, lx, ly);
+        bool valid = P.preview ? slot_preview(P, q, lx, ly) : slot_pixel(P, q, lx, ly);
         if (valid) {
             PathRegs ps;
-            ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
+            if (P.preview) ps.ray = preview_ray(P, lx, P.pv_y0 + ly, ps.rng);
+            else ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
             ps.thr = mk3(1.0f); ps.rad = mk3(0.0f); ps.absn = mk3(0.0f); ps.bsdf_pdf = 0.f;
             ps.stale = xyz(ldg4(S.materials + 1));                 // State is zero-filled: matID 0's emission (pathtrace.glsl:213,253)
             store_state(A, s, ps);
@@ -485,6 +495,18 @@ __global__ void __launch_bounds__(256) k_accumulate(DevParams P, PathSoA A, floa
     }
 }
 
+// The preview target is written, not accumulated (preview_flareon.glsl:60; TiledRenderer.cpp:329-331).
+__global__ void __launch_bounds__(256) k_preview_store(DevParams P, PathSoA A, float* __restrict__ preview) {
+    int n = P.pv_w * P.tile_h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int lx = i % P.pv_w, ly = i / P.pv_w;
+        if (P.pv_y0 + ly >= P.pv_h) continue;
+        float4 c = A.rad[pixel_slot(P, lx, ly)];
+        float* o = preview + 3 * ((size_t)(P.pv_y0 + ly) * P.pv_w + lx);
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- megakernel
 // The same device functions, one thread per pixel-sample for the whole path (kernel_mode = 1).
 template <bool CULL, bool COUNT, int STACK>
@@ -681,6 +703,12 @@ void launch_accumulate(const LaunchCtx& L, float* accum) {
     int blocks = (n + 255) / 256;
     if (blocks > L.sm_count * 8) blocks = L.sm_count * 8;
     k_accumulate<<<blocks, 256, 0, L.stream>>>(L.params, L.soa, accum);
+}
+void launch_preview_store(const LaunchCtx& L, float* preview) {
+    int n = L.params.pv_w * L.params.tile_h;
+    int blocks = (n + 255) / 256;
+    if (blocks > L.sm_count * 8) blocks = L.sm_count * 8;
+    k_preview_store<<<blocks, 256, 0, L.stream>>>(L.params, L.soa, preview);
 }
 template <bool CULL, bool COUNT>
 static void launch_mega_s(const LaunchCtx& L, int blocks) {

@@ -24,6 +24,7 @@ void launch_shade(const LaunchCtx& L, int depth);
 void launch_sample(const LaunchCtx& L, int depth);
 void launch_shadow(const LaunchCtx& L, int depth);
 void launch_accumulate(const LaunchCtx& L, float* accum);
+void launch_preview_store(const LaunchCtx& L, float* preview);
 void launch_megakernel(const LaunchCtx& L);
 void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* emitter);
 void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int passes, float* sink, int blocks);

@@ -74,6 +74,8 @@ struct DevParams {
     int   first_frame, frame_stride, num_frames;   // frames of the current batch
     int   pix_w8, pix_h4;                 // tile size rounded up to 8x4 pixel blocks (warp-coherent primary rays)
     int   slots_per_frame;                // pix_w8 * pix_h4
+    // preview engine (shaders/preview_flareon.glsl): the batch is rows [pv_y0, pv_y0 + tile_h) of a pv_w x pv_h viewport
+    int   preview, pv_w, pv_h, pv_y0, use_dof;
 };
 
 // Per-path state, structure of arrays; one slot = one pixel-sample of the batch.

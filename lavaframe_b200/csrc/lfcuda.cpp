@@ -72,6 +72,8 @@ struct lfcuda_ctx {
     Queues queues{};
     float* d_accum = nullptr; size_t accum_floats = 0;
     float* d_out_f = nullptr; unsigned char* d_out_u8 = nullptr;
+    float* d_preview = nullptr; float* d_preview_out = nullptr;   // preview engine target (pathTraceTextureLowRes) + its post-processed copy
+    size_t preview_cap = 0; int preview_w = 0, preview_h = 0;
     DevCounters* d_counters = nullptr;
 
     // instrumentation
@@ -132,6 +134,7 @@ void free_state(lfcuda_ctx* c) {
     c->state_allocs.clear();
     c->capacity = 0;
     c->d_accum = nullptr; c->d_out_f = nullptr; c->d_out_u8 = nullptr;
+    c->d_preview = nullptr; c->d_preview_out = nullptr; c->preview_cap = 0; c->preview_w = c->preview_h = 0;
 }
 
 int alloc_state(lfcuda_ctx* ctx) {
@@ -164,7 +167,7 @@ int alloc_state(lfcuda_ctx* ctx) {
     if ((r = A((void**)&ctx->queues.active[1], cap * sizeof(int)))) return r;
     if ((r = A((void**)&ctx->queues.shadow, cap * sizeof(int)))) return r;
     if ((r = A((void**)&ctx->queues.sample, cap * sizeof(int)))) return r;
-    ctx->queues.stride = P.max_depth + 2;
+    ctx->queues.stride = std::max(P.max_depth, 2) + 2;   // the preview engine runs at depth 2 whatever maxDepth is (TiledRenderer.cpp:532)
     if ((r = A((void**)&ctx->queues.counts, (size_t)kCountRows * ctx->queues.stride * sizeof(int)))) return r;
     ctx->accum_floats = (size_t)P.width * P.height * 3;
     if ((r = A((void**)&ctx->d_accum, ctx->accum_floats * sizeof(float)))) return r;
@@ -484,6 +487,67 @@ int lfcuda_render_frames(lfcuda_ctx* ctx, int32_t first_frame, int32_t nframes, 
         if (r) return r;
         done += n;
     }
+    return 0;
+}
+
+// Preview engine: TiledRenderer::Render while camera->isMoving || instancesModified (TiledRenderer.cpp:327-333).
+int lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, int32_t max_depth, int32_t use_dof) {
+    int r = check_ready(ctx);
+    if (r) return r;
+    if (pv_width < 1 || pv_height < 1 || max_depth < 1) return fail(ctx, LFCUDA_EINVAL, "preview size and depth must be positive");
+    if (max_depth + 2 > ctx->queues.stride) return fail(ctx, LFCUDA_EINVAL, "preview depth %d exceeds the depth the path state was sized for (%d)", max_depth, ctx->queues.stride - 2);
+    CK(cudaSetDevice(ctx->device));
+    const size_t need = (size_t)pv_width * pv_height * 3;
+    if (need > ctx->preview_cap) {
+        // grown on demand (previewScale changes reload the renderer in the reference, Main.cpp:525); freed with the path state
+        CK(cudaStreamSynchronize(ctx->stream));
+        float *a = nullptr, *b = nullptr;
+        CK(cudaMalloc((void**)&a, need * sizeof(float)));
+        ctx->state_allocs.push_back(a);
+        CK(cudaMalloc((void**)&b, need * sizeof(float)));
+        ctx->state_allocs.push_back(b);
+        ctx->d_preview = a; ctx->d_preview_out = b; ctx->preview_cap = need;
+    }
+    ctx->preview_w = pv_width; ctx->preview_h = pv_height;
+    const int w8 = (pv_width + 7) / 8 * 8;
+    int band = (int)std::min<size_t>((size_t)pv_height, ctx->capacity / (size_t)w8) / 4 * 4;   // rows per batch, whole 8x4 blocks
+    if (band < 4) return fail(ctx, LFCUDA_ELIMIT, "preview row of %d pixels does not fit the path state (%zu slots)", pv_width, ctx->capacity);
+    for (int y0 = 0; y0 < pv_height; y0 += band) {
+        const int rows = std::min(band, pv_height - y0);
+        DevParams D;
+        fill_dev_params(ctx, D, 1, 1, 1, 0, 0);
+        D.preview = 1; D.pv_w = pv_width; D.pv_h = pv_height; D.pv_y0 = y0; D.use_dof = use_dof ? 1 : 0;
+        D.max_depth = max_depth;
+        D.tile_w = pv_width; D.tile_h = rows;
+        D.pix_w8 = w8; D.pix_h4 = (rows + 3) / 4 * 4; D.slots_per_frame = D.pix_w8 * D.pix_h4;
+        LaunchCtx L;
+        make_launch_ctx(ctx, L, D);
+        CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)kCountRows * ctx->queues.stride * sizeof(int), ctx->stream));
+        { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
+        for (int d = 0; d < D.max_depth; d++) {
+            { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, d); }
+            { StageTimer t(ctx, LF_STAGE_SHADE); launch_shade(L, d); }
+            if (d + 1 < D.max_depth) { StageTimer t(ctx, LF_STAGE_SAMPLE); launch_sample(L, d); }
+            { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
+        }
+        { StageTimer t(ctx, LF_STAGE_ACCUMULATE); launch_preview_store(L, ctx->d_preview); }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// The preview target through the post-process pass, as Present()/SetViewport() show it (TiledRenderer.cpp:361-364,558-562;
+// invSampleCounter = 1 because Update() has reset sampleCounter to 1, :475).  pv_width * pv_height * 3 floats, rows bottom-up.
+int lfcuda_read_preview(lfcuda_ctx* ctx, int32_t tonemap_index, float* rgb_out) {
+    if (!ctx || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "NULL context or output");
+    if (!ctx->d_preview || ctx->preview_w < 1) return fail(ctx, LFCUDA_EINVAL, "no preview rendered (lfcuda_render_preview)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->preview_w * ctx->preview_h * 3;
+    ctx->launches++;
+    launch_post(ctx->stream, ctx->d_preview, ctx->d_preview_out, nullptr, ctx->preview_w, ctx->preview_h, 1.0f, tonemap_index, ctx->post);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb_out, ctx->d_preview_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

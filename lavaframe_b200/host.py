@@ -40,6 +40,10 @@ class HostScene:
     def set_camera_moving(self, moving):
         self.lib.lfhost_set_camera_moving(self.h, 1 if moving else 0)
 
+    def set_preview(self, scale=1.0, use_dof=False):
+        """GlobalState.previewScale / useDofInPreview (Main.cpp:525-529); read by the renderer's Init like TiledRenderer.cpp:61,90."""
+        self.lib.lfhost_set_preview(float(scale), 1 if use_dof else 0)
+
     def close(self):
         if self.h:
             self.lib.lfhost_free_scene(self.h)
@@ -96,6 +100,15 @@ class CudaRenderer:
         out = np.empty((p.height, p.width, 3), np.uint8)
         w, h = C.c_int(), C.c_int()
         self.lib.lfhost_renderer_output_u8(self.h, out.ctypes.data_as(C.c_void_p), C.byref(w), C.byref(h))
+        return out
+
+    def GetPreviewBufferHDR(self):
+        """What Present()/SetViewport() show while the camera moves: the preview engine's image, or None."""
+        w, h = C.c_int(), C.c_int()
+        if self.lib.lfhost_renderer_preview_hdr(self.h, None, C.byref(w), C.byref(h)) != 0:
+            return None
+        out = np.empty((h.value, w.value, 3), np.float32)
+        self.lib.lfhost_renderer_preview_hdr(self.h, out.ctypes.data_as(C.c_void_p), C.byref(w), C.byref(h))
         return out
 
     def context_handle(self):

@@ -9,8 +9,11 @@
 #include <cstdio>
 
 #include "Camera.h"
+#include "GlobalState.h"
 #include "Scene.h"
 #include "scene_view.h"
+
+extern LavaFrameState GlobalState;
 
 namespace LavaFrame
 {
@@ -20,6 +23,7 @@ namespace LavaFrame
         , tileX(-1), tileY(-1), numTilesX(-1), numTilesY(-1)
         , tileWidth(scene->renderOptions.tileWidth), tileHeight(scene->renderOptions.tileHeight)
         , currentBuffer(0), frameCounter(1), sampleCounter(0)
+        , pixelRatio(1.0f), previewDof(false), previewDepth(2), previewW(0), previewH(0)
     {
     }
 
@@ -44,6 +48,10 @@ namespace LavaFrame
         numTilesY = (int)ceil((float)screenSize.y / tileHeight);
         tileX = -1;
         tileY = numTilesY - 1;
+        pixelRatio = GlobalState.previewScale;               // :61
+        previewDof = GlobalState.useDofInPreview;            // :90-91
+        previewDepth = scene->renderOptions.maxDepth;
+        previewW = previewH = 0;
 
         if (lfcuda_create(&ctx, device) != 0) {
             error = lfcuda_last_error(nullptr);
@@ -110,7 +118,12 @@ namespace LavaFrame
     {
         if (!initialized) { printf("Renderer is not initialized.\n"); return; }   // TiledRenderer.cpp:319-323
         if (scene->camera->isMoving || scene->instancesModified) {
-            scene->instancesModified = false;    // the reference draws its low-res preview here (:325-333); no preview when headless
+            // previewEngineShader into previewFBO (:327-333); glViewport truncates the float sizes to GLsizei
+            const int pw = (int)(screenSize.x * pixelRatio), ph = (int)(screenSize.y * pixelRatio);
+            if (lfcuda_render_preview(ctx, pw, ph, previewDepth, previewDof ? 1 : 0) != 0)
+                printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+            else { previewW = pw; previewH = ph; }
+            scene->instancesModified = false;
             return;
         }
         pending.push_back(Step{frameCounter, tileX, tileY, sampleCounter});
@@ -157,6 +170,17 @@ namespace LavaFrame
             }
         }
         UploadUniforms();                                            // :505-521 (camera, maxDepth, hdrMultiplier, bgColor ...)
+        previewDepth = (scene->camera->isMoving || scene->instancesModified) ? 2 : scene->renderOptions.maxDepth;   // :532
+    }
+
+    void CudaRenderer::GetPreviewBufferHDR(float** data, int& w, int& h)
+    {
+        w = previewW; h = previewH;
+        *data = nullptr;
+        if (!initialized || previewW < 1) return;
+        *data = new float[(size_t)w * h * 3];
+        if (lfcuda_read_preview(ctx, scene->renderOptions.tonemapIndex, *data) != 0)
+            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
     }
 
     void CudaRenderer::GetOutputBufferHDR(float** data, int& w, int& h)

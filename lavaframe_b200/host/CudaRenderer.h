@@ -43,6 +43,10 @@ namespace LavaFrame
         lfcuda_ctx* Context() const { return ctx; }
         const char* LastError() const;
         void Flush();                                            // execute every queued tile step now
+        // The image Present()/SetViewport() display while the camera moves or before the first sample completes
+        // (pathTraceTextureLowRes through postShader, TiledRenderer.cpp:361-364,558-562): w x h x 3 floats, bottom row
+        // first, allocated with new[] like GetOutputBufferHDR.  *data is nullptr when no preview has been drawn.
+        void GetPreviewBufferHDR(float** data, int& w, int& h);
 
     private:
         struct Step { int frame, tileX, tileY, sample; };
@@ -56,6 +60,10 @@ namespace LavaFrame
 
         int tileX, tileY, numTilesX, numTilesY, tileWidth, tileHeight;
         int currentBuffer, frameCounter, sampleCounter;
+        float pixelRatio;                // GlobalState.previewScale at Init (TiledRenderer.cpp:61)
+        bool previewDof;                 // GlobalState.useDofInPreview at Init (#define USE_DOF, :90-91)
+        int previewDepth;                // the preview shader's maxDepth uniform as Update last set it (:532)
+        int previewW, previewH;          // size of the last preview drawn, 0 = none
         std::string error;
     };
 }

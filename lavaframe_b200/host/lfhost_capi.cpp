@@ -100,6 +100,16 @@ int lfhost_renderer_output_u8(void* r, unsigned char* out, int* w, int* h) {
     delete[] data;
     return 0;
 }
+// The preview image (CudaRenderer::GetPreviewBufferHDR); with out == NULL only the size is returned.  -1 = no preview drawn.
+int lfhost_renderer_preview_hdr(void* r, float* out, int* w, int* h) {
+    float* data = nullptr;
+    static_cast<CudaRenderer*>(r)->GetPreviewBufferHDR(&data, *w, *h);
+    if (!data) return -1;
+    if (out) std::memcpy(out, data, (size_t)(*w) * (*h) * 3 * sizeof(float));
+    delete[] data;
+    return 0;
+}
+void lfhost_set_preview(float scale, int use_dof) { GlobalState.previewScale = scale; GlobalState.useDofInPreview = use_dof != 0; }   // Main.cpp:525-529
 // Main.cpp's loop (MainLoop :313-755 -> Update :160-234 -> Render :99-158) for `spp` samples: the auto-stop test
 // `maxSamples + 1 == GetSampleCount()` comes first, then renderer->Update, then renderer->Render.
 int lfhost_renderer_run(void* rv, int spp) {

@@ -995,6 +995,41 @@ static Ray CameraRay(Inv& g, int lx, int ly, int tileX, int tileY, int frame, in
     return {pos + randomAperturePos, finalRayDir};
 }
 
+// preview_flareon.glsl:22-61: the camera ray of fragment (x, y) of the pvW x pvH preview viewport.  Differences from
+// renderer.glsl: RNG seeded with gl_FragCoord.xy and frame 1 (:24), jitter divided by the full screenResolution (:33),
+// d = 2 * TexCoords - 1 (no tile mapping, :34), and the thin lens only under #define USE_DOF (:44-57) although its two
+// rand() are always drawn (:42-43).
+static Ray PreviewRay(Inv& g, int x, int y, int pvW, int pvH, bool useDof) {
+    const Oracle* o = g.o;
+    const LfParams& P = o->params;
+    const LfCamera& C = o->camera;
+    vec2 screenResolution = {(float)P.width, (float)P.height};
+    vec2 TexCoords = {((float)x + 0.5f) / (float)pvW, ((float)y + 0.5f) / (float)pvH};
+    InitRNG(g, vec2{(float)x + 0.5f, (float)y + 0.5f}, 1);
+    float r1 = 2.0f * rnd(g);
+    float r2 = 2.0f * rnd(g);
+    vec2 jitter;
+    jitter.x = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
+    jitter.y = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
+    jitter.x /= screenResolution.x;
+    jitter.y /= screenResolution.y;
+    vec2 d = {(2.0f * TexCoords.x - 1.0f) + jitter.x, (2.0f * TexCoords.y - 1.0f) + jitter.y};
+    float scale = tanf(C.fov * 0.5f);
+    d.y *= screenResolution.y / screenResolution.x * scale;
+    d.x *= scale;
+    vec3 right = {C.right[0], C.right[1], C.right[2]}, up = {C.up[0], C.up[1], C.up[2]}, fwd = {C.forward[0], C.forward[1], C.forward[2]};
+    vec3 pos = {C.position[0], C.position[1], C.position[2]};
+    vec3 rayDir = normalize(d.x * right + d.y * up + fwd);
+    vec3 focalPoint = C.focal_dist * rayDir;
+    float cam_r1 = rnd(g) * TWO_PI;
+    float cam_r2 = rnd(g) * C.aperture;
+    if (!useDof) return {pos, normalize(focalPoint)};
+    float sl, cl;
+    lfom::sincos(cam_r1, sl, cl);
+    vec3 randomAperturePos = (cl * right + sl * up) * sqrtf(cam_r2);
+    return {pos + randomAperturePos, normalize(focalPoint - randomAperturePos)};
+}
+
 // ------------------------------------------------------------------------------------------------
 // Oracle
 // ------------------------------------------------------------------------------------------------
@@ -1043,6 +1078,23 @@ void Oracle::RenderFrames(int firstFrame, int nframes, int frameStride, int tile
         addCounters(total, local);
     }
     addCounters(counters, total);
+}
+
+// One draw of previewEngineShader into the pvW x pvH preview target (TiledRenderer.cpp:327-333) with uniform maxDepth
+// (2 while the camera moves, :532).  out = pvW * pvH * 3 floats, rows bottom-up; nothing is accumulated.
+void Oracle::RenderPreview(int pvW, int pvH, int maxDepth, bool useDof, float* out) {
+    LfParams saved = params;
+    params.max_depth = maxDepth;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < pvW * pvH; i++) {
+        Inv g;
+        std::memset(&g, 0, sizeof g);
+        g.o = this;
+        Ray ray = PreviewRay(g, i % pvW, i / pvW, pvW, pvH, useDof);
+        vec3 c = PathTrace(g, ray);
+        out[3 * (size_t)i] = c.x; out[3 * (size_t)i + 1] = c.y; out[3 * (size_t)i + 2] = c.z;
+    }
+    params = saved;
 }
 
 void Oracle::PrimaryHits(int frame, float* t, int32_t* triX, int32_t* matID, int32_t* emitter) {

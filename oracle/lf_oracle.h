@@ -36,6 +36,10 @@ struct Oracle {
     // nframes draws of one tile, each added to accum (W*H*3, rows bottom-up) in frame order; OpenMP over pixels.
     void RenderFrames(int firstFrame, int nframes, int frameStride, int tileX, int tileY, float* accum);
 
+    // The preview engine (shaders/preview_flareon.glsl:22-61): one sample per pixel of a pvW x pvH viewport, frame 1,
+    // no accumulation.  out = pvW * pvH * 3 floats, rows bottom-up.
+    void RenderPreview(int pvW, int pvH, int maxDepth, bool useDof, float* out);
+
     // Probe 1: ClosestHit of the first camera ray of `frame` for every pixel of the full frame (single tile
     // covering the frame), like the llvmpipe "--probe hits" shader variant.
     void PrimaryHits(int frame, float* t, int32_t* triX, int32_t* matID, int32_t* emitter);

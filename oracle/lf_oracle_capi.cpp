@@ -44,6 +44,9 @@ void lforacle_set_options(void* hv, int cull, int count) {
 void lforacle_render_frames(void* hv, int first_frame, int nframes, int frame_stride, int tile_x, int tile_y, float* accum) {
     static_cast<Handle*>(hv)->oracle->RenderFrames(first_frame, nframes, frame_stride, tile_x, tile_y, accum);
 }
+void lforacle_render_preview(void* hv, int pv_w, int pv_h, int max_depth, int use_dof, float* out) {
+    static_cast<Handle*>(hv)->oracle->RenderPreview(pv_w, pv_h, max_depth, use_dof != 0, out);
+}
 void lforacle_primary_hits(void* hv, int frame, float* t, int32_t* tri, int32_t* mat, int32_t* emitter) {
     static_cast<Handle*>(hv)->oracle->PrimaryHits(frame, t, tri, mat, emitter);
 }

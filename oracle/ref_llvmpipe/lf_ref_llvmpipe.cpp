@@ -104,7 +104,8 @@ static double now() {
 int main(int argc, char** argv) {
     std::string sceneFile, out = "out.f32", probe, extractDir, shadersOverride;
     int spp = 1;
-    bool timingJson = false;
+    bool timingJson = false, previewDof = false;
+    float previewScale = 0.f;                        // > 0: render the preview engine's image instead (--preview SCALE)
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { return i + 1 < argc ? argv[++i] : ""; };
@@ -115,6 +116,8 @@ int main(int argc, char** argv) {
         else if (a == "--extract-assets") extractDir = next();
         else if (a == "--shaders") shadersOverride = next();
         else if (a == "--timing-json") timingJson = true;
+        else if (a == "--preview") previewScale = (float)atof(next().c_str());
+        else if (a == "--preview-dof") previewDof = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     if (!extractDir.empty()) {
@@ -187,6 +190,8 @@ int main(int argc, char** argv) {
     GlobalState.scene->renderOptions = ro;          // Main.cpp:969
     GlobalState.scene->camera->isMoving = false;    // never initialised by Camera's ctor (Camera.cpp:101-117)
 
+    if (previewScale > 0.f) { GlobalState.previewScale = previewScale; GlobalState.useDofInPreview = previewDof; }   // Main.cpp:525-529
+
     double t0 = now();
     TiledRenderer* r = new TiledRenderer(GlobalState.scene, GlobalState.shadersDir);
     GlobalState.renderer = r;
@@ -198,6 +203,26 @@ int main(int argc, char** argv) {
     }
     glFinish();
     double t1 = now();
+
+    if (previewScale > 0.f) {
+        // What the main loop does while the camera moves (Main.cpp:233,101): Update resets the counters and sets
+        // maxDepth 2 (TiledRenderer.cpp:471-484,532), Render draws previewEngineShader into previewFBO (:327-333), whose
+        // colour attachment (pathTraceTextureLowRes, RGB32F) is read back here while the FBO is still bound.
+        GlobalState.scene->camera->isMoving = true;
+        r->Update(0.f);
+        r->Render();
+        glFinish();
+        const iVec2 ss = r->GetScreenSize();
+        const int pw = (int)(ss.x * previewScale), ph = (int)(ss.y * previewScale);   // glViewport's float -> GLsizei (:330)
+        std::vector<float> img((size_t)pw * ph * 3);
+        glReadPixels(0, 0, pw, ph, GL_RGB, GL_FLOAT, img.data());
+        FILE* f = fopen(out.c_str(), "wb");
+        if (!f) { perror(out.c_str()); return 6; }
+        fwrite(img.data(), sizeof(float), img.size(), f);
+        fclose(f);
+        printf("preview %dx%d (scale %g, dof %d) written; glGetError 0x%x\n", pw, ph, previewScale, (int)previewDof, glGetError());
+        return 0;
+    }
 
     std::vector<double> stepTimes;
     while (true) {                                   // Main.cpp MainLoop: Update (auto-stop check first) then Render

@@ -13,7 +13,11 @@ and lavaframe_b200/bin/lf_scenepack by CMake):
   * cornell_llvmpipe_4096spp.npz   the converged reference image for the north_star's third check (20 min of llvmpipe):
         spp4096 = mean of frames 2..4097
 
-Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [cornell4096] ...
+  * <name>_llvmpipe_preview.npz    the preview engine's image (shaders/preview_flareon.glsl drawn by TiledRenderer::Render
+        while camera->isMoving, read back from previewFBO): half = previewScale 0.5, maxDepth 2;
+        full_dof = previewScale 1.0 with "#define USE_DOF"
+
+Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [cornell4096] [preview] ...
 """
 import json
 import os
@@ -56,7 +60,26 @@ def converged_cornell(spp=4096):
         print("cornell", spp, "spp mean", img.mean(axis=(0, 1)), "render_s", info["render_s"])
 
 
+def preview_goldens():
+    for name, (builder, _) in SCENES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            scene = builder(os.path.join(tmp, "assets"))
+            arrays = {}
+            for key, scale, dof in (("half", 0.5, False), ("full_dof", 1.0, True)):
+                out = os.path.join(tmp, key + ".f32")
+                cmd = [REFBIN, "--scene", scene, "--out", out, "--preview", str(scale)] + (["--preview-dof"] if dof else [])
+                res = subprocess.run(cmd, env=gen_scenes.llvmpipe_env(), check=True, capture_output=True, text=True)
+                line = [l for l in res.stdout.splitlines() if l.startswith("preview ")][-1]
+                pw, ph = (int(v) for v in line.split()[1].split("x"))
+                arrays[key] = np.fromfile(out, np.float32).reshape(ph, pw, 3)
+                print(name, line, "mean", arrays[key].mean(axis=(0, 1)))
+            np.savez_compressed(os.path.join(GOLD, f"{name}_llvmpipe_preview.npz"), **arrays)
+
+
 def main(names):
+    if "preview" in names:
+        preview_goldens()
+        names = [n for n in names if n != "preview"]
     if "cornell4096" in names:
         converged_cornell(4096)
         names = [n for n in names if n != "cornell4096"]

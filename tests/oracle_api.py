@@ -33,6 +33,7 @@ def load_oracle():
     lib.lforacle_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lforacle_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.lforacle_render_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lforacle_render_preview.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lforacle_primary_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lforacle_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lforacle_rand_kat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -69,6 +70,12 @@ class Oracle:
             accum = np.zeros((self.params.height, self.params.width, 3), np.float32)
         self.lib.lforacle_render_frames(self.h, first_frame, nframes, frame_stride, tile_x, tile_y, accum.ctypes.data_as(C.c_void_p))
         return accum
+
+    def render_preview(self, pv_w, pv_h, max_depth=2, use_dof=False):
+        """preview_flareon.glsl: one sample per pixel of a pv_w x pv_h viewport, frame 1, rows bottom-up."""
+        out = np.zeros((pv_h, pv_w, 3), np.float32)
+        self.lib.lforacle_render_preview(self.h, pv_w, pv_h, max_depth, int(use_dof), out.ctypes.data_as(C.c_void_p))
+        return out
 
     def primary_hits(self, frame=2):
         H, W = self.params.height, self.params.width

@@ -113,6 +113,32 @@ def test_converged_4096spp_vs_llvmpipe(tracer, golden_dir):
 
 
 @pytest.mark.parametrize("name", SCENES)
+def test_preview_engine(tracer, golden_dir, oracle_lib, name):
+    """SURVEY 8(f) row 3, shaders/preview_flareon.glsl: lfcuda_render_preview against the oracle (bit for bit: the same
+    wavefront kernels at another launch shape) and against the preview the unmodified reference drew on llvmpipe.  Also
+    an odd size that ends in partial 8x4 blocks, at the scene's full depth, and that a preview leaves the accumulation
+    buffer untouched."""
+    pack = lf.ScenePack(pack_path(golden_dir, name))
+    tracer.upload_pack(pack)
+    tracer.clear()
+    tracer.render_frames(2, 2)
+    accum = tracer.read_accum()
+    g = np.load(os.path.join(golden_dir, f"{name}_llvmpipe_preview.npz"))
+    o = Oracle(pack.path)
+    for key, dof in (("half", False), ("full_dof", True)):
+        h, w, _ = g[key].shape
+        img = tracer.render_preview(w, h, 2, dof)
+        ref = o.render_preview(w, h, 2, dof)
+        assert np.array_equal(img, ref), f"{name}/{key}: {int((img != ref).any(axis=2).sum())} pixels differ from the oracle"
+        frac = radiance_agreement(img, g[key])
+        assert frac >= MIN_VS_LLVMPIPE[name] - 0.01, f"{name}/{key}: within 1e-3 of llvmpipe on {frac:.6f}"
+    img = tracer.render_preview(77, 45, pack.max_depth, False)
+    assert np.array_equal(img, o.render_preview(77, 45, pack.max_depth, False))
+    o.close()
+    assert np.array_equal(tracer.read_accum(), accum)
+
+
+@pytest.mark.parametrize("name", SCENES)
 def test_wavefront_equals_megakernel(tracer, golden_dir, name):
     """Two kernel organisations of the same device functions must agree bit for bit."""
     pack = lf.ScenePack(pack_path(golden_dir, name))

@@ -97,3 +97,33 @@ def test_instance_edit_path(cornell_scene, golden_dir):
     r.Run(2)
     assert np.array_equal(r.GetOutputBufferHDR(), before)
     r.close()
+
+
+def test_preview_while_camera_moves(cornell_scene, golden_dir):
+    """TiledRenderer::Render draws the preview engine while camera->isMoving (TiledRenderer.cpp:327-333) at
+    screenSize * GlobalState.previewScale; the image Present() would show must equal the reference's previewFBO."""
+    g = np.load(os.path.join(golden_dir, "cornell_llvmpipe_preview.npz"))
+    cornell_scene.set_preview(0.5, False)
+    r = lf.CudaRenderer(cornell_scene)
+    assert r.GetPreviewBufferHDR() is None
+    r.Run(2)
+    cornell_scene.set_camera_moving(True)
+    r.Update(0.0); r.Render()
+    img = r.GetPreviewBufferHDR()
+    cornell_scene.set_camera_moving(False)
+    assert img.shape == g["half"].shape
+    assert radiance_agreement(img, g["half"]) >= 0.999
+    r.Run(2)                                             # and the path tracer restarts from a cleared accumulation
+    a = r.GetOutputBufferHDR()
+    r.close()
+    cornell_scene.set_preview(1.0, True)
+    r = lf.CudaRenderer(cornell_scene)
+    cornell_scene.set_camera_moving(True)
+    r.Update(0.0); r.Render()
+    img = r.GetPreviewBufferHDR()
+    cornell_scene.set_camera_moving(False)
+    assert radiance_agreement(img, g["full_dof"]) >= 0.999
+    r.Run(2)
+    assert np.array_equal(a, r.GetOutputBufferHDR())
+    r.close()
+    cornell_scene.set_preview(1.0, False)

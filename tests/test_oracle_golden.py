@@ -146,3 +146,26 @@ def test_cull_preserves_results(golden_dir, oracle_lib, name):
         assert np.array_equal(x, y)
     assert np.array_equal(a.render_frames(2, 2), b.render_frames(2, 2))
     a.close(); b.close()
+
+
+# Same reasoning as MIN_SPP1: the Cornell box is pinned at the north_star bar, glass / metal / textures cannot be.
+MIN_PREVIEW = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.97}
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_preview_engine_vs_llvmpipe(golden_dir, oracle_lib, name):
+    """SURVEY 8(f) row 3: shaders/preview_flareon.glsl as TiledRenderer::Render draws it while the camera moves
+    (read back from previewFBO of the unmodified reference on llvmpipe) against the oracle's RenderPreview."""
+    gold = os.path.join(golden_dir, f"{name}_llvmpipe_preview.npz")
+    if not os.path.exists(gold):
+        pytest.skip(f"{gold} not generated")
+    g = np.load(gold)
+    o = Oracle(_pack(golden_dir, name))
+    for key, dof in (("half", False), ("full_dof", True)):
+        ref = g[key]
+        h, w, _ = ref.shape
+        img = o.render_preview(w, h, 2, dof)
+        frac = radiance_agreement(img, ref)
+        assert frac >= MIN_PREVIEW[name], f"{name}/{key}: preview radiance within 1e-3 on {frac:.6f} of pixels"
+        assert rmse_over_mean_luminance(img, ref) < 0.05
+    o.close()
