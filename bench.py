@@ -7,8 +7,8 @@
 Workload (config.workload): BASELINE.json configs[1] = C2, the "dragon-class" 869 880-triangle mesh instanced as Disney
 metal and glass over a textured ground quad under an importance-sampled 2048x1024 HDR environment, 1280x720, max depth 6
 (scenes/gen_scenes.py: c2_full; synthetic, generated on the spot and flattened by the reference's unchanged loader + BVH
-builder).  One STEP = one pass of the hot path over one batch: --spp-per-step (16) samples for every pixel of the frame
-(14.7 M pixel-samples); the default 64 steps are the config's full 1024 spp.
+builder).  One STEP = one pass of the hot path over one batch: --spp-per-step (32) samples for every pixel of the frame
+(29.5 M pixel-samples); the default 32 steps are the config's full 1024 spp.
 
   value      whole-job samples/s, scene resident in HBM, timed with CUDA events on the launching stream, barrier +
              synchronize on both sides, max over ranks.  N > 1: every rank renders its own frame numbers (frame = RNG seed,
@@ -195,11 +195,11 @@ class _DevBuf:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c2_full", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--spp-per-step", type=int, default=32)
     ap.add_argument("--kernel-mode", type=int, default=0, help="0 wavefront (default), 1 megakernel")
     ap.add_argument("--frames-in-flight", type=int, default=0, help="pixel-sample frames per wavefront batch (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -275,8 +275,8 @@ def main():
     stats0 = pt.stage_stats()
     launches0 = pt.launch_count()
     sampler = ClockSampler(local_rank)
-    barrier(); sync()
-    sampler.start()
+    sampler.start()                                    # before the barrier: forking nvidia-smi takes tens of ms, different on every
+    barrier(); sync()                                  # rank, and would skew the ranks' start times inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(K):

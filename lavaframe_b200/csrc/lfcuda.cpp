@@ -144,9 +144,10 @@ int alloc_state(lfcuda_ctx* ctx) {
     ctx->pix_h4 = (P.tile_height + 3) / 4 * 4;
     ctx->slots_per_frame = ctx->pix_w8 * ctx->pix_h4;
     int F = P.frames_in_flight;
-    if (F <= 0) {   // auto: about 16 M pixel-samples in flight (4.5 GB of path state), at least one frame.  Measured on C2:
-                    // 4 M -> 328, 8 M -> 360, 16 M -> 377 M samples/s: deep bounces keep enough rays to fill the persistent grid.
-        F = (int)((size_t)(16u << 20) / (size_t)ctx->slots_per_frame);
+    if (F <= 0) {   // auto: about 32 M pixel-samples in flight (11 GB of path state of 180 GB), at least one frame.  Measured on C2:
+                    // 4 M -> 328, 8 M -> 360, 16 M -> 377 M samples/s with the first kernels, 16 M -> 427, 32 M -> 435, 64 M -> 436 with
+                    // the final ones: deep bounces keep enough rays to fill the persistent grid.
+        F = (int)((size_t)(32u << 20) / (size_t)ctx->slots_per_frame);
         if (F < 1) F = 1;
         if (F > 256) F = 256;
     }
