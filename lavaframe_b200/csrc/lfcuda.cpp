@@ -502,6 +502,12 @@ int lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, 
     if (need > ctx->preview_cap) {
         // grown on demand (previewScale changes reload the renderer in the reference, Main.cpp:525); freed with the path state
         CK(cudaStreamSynchronize(ctx->stream));
+        for (float* old : {ctx->d_preview, ctx->d_preview_out}) {   // a smaller pair from an earlier previewScale
+            if (!old) continue;
+            cudaFree(old);
+            ctx->state_allocs.erase(std::remove(ctx->state_allocs.begin(), ctx->state_allocs.end(), (void*)old), ctx->state_allocs.end());
+        }
+        ctx->d_preview = ctx->d_preview_out = nullptr; ctx->preview_cap = 0;
         float *a = nullptr, *b = nullptr;
         CK(cudaMalloc((void**)&a, need * sizeof(float)));
         ctx->state_allocs.push_back(a);

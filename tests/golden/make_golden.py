@@ -17,7 +17,7 @@ and lavaframe_b200/bin/lf_scenepack by CMake):
         while camera->isMoving, read back from previewFBO): half = previewScale 0.5, maxDepth 2;
         full_dof = previewScale 1.0 with "#define USE_DOF"
 
-Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [cornell4096] [preview] ...
+Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [cornell4096] [preview] [tiled] ...
 """
 import json
 import os
@@ -60,6 +60,21 @@ def converged_cornell(spp=4096):
         print("cornell", spp, "spp mean", img.mean(axis=(0, 1)), "render_s", info["render_s"])
 
 
+def tiled_cornell(spp=4, tile=64):
+    """cornell_tiled_llvmpipe.npz: the Cornell scene with `tileWidth 64 / tileHeight 64` (Loader.cpp:256-261), `spp` samples =
+    spp * 16 tile steps; every tile step advances `frame` (TiledRenderer.cpp:485-487), so the RNG seeds differ from the untiled run."""
+    with tempfile.TemporaryDirectory() as tmp:
+        scene = gen_scenes.cornell_256(os.path.join(tmp, "assets"))
+        text = open(scene).read()
+        tiled = os.path.join(os.path.dirname(scene), "cornell_tiled.scene")
+        open(tiled, "w").write(text.replace("resolution 256 256", f"resolution 256 256\n\ttileWidth {tile}\n\ttileHeight {tile}"))
+        out = os.path.join(tmp, "tiled.f32")
+        info = run_ref(tiled, spp, out)
+        img = np.fromfile(out, np.float32).reshape(info["height"], info["width"], 3)
+        np.savez_compressed(os.path.join(GOLD, "cornell_tiled_llvmpipe.npz"), sppN=img, nspp=np.int32(spp), tile=np.int32(tile))
+        print("cornell tiled", spp, "spp mean", img.mean(axis=(0, 1)), info)
+
+
 def preview_goldens():
     for name, (builder, _) in SCENES.items():
         with tempfile.TemporaryDirectory() as tmp:
@@ -80,6 +95,9 @@ def main(names):
     if "preview" in names:
         preview_goldens()
         names = [n for n in names if n != "preview"]
+    if "tiled" in names:
+        tiled_cornell()
+        names = [n for n in names if n != "tiled"]
     if "cornell4096" in names:
         converged_cornell(4096)
         names = [n for n in names if n != "cornell4096"]

@@ -169,3 +169,30 @@ def test_preview_engine_vs_llvmpipe(golden_dir, oracle_lib, name):
         assert frac >= MIN_PREVIEW[name], f"{name}/{key}: preview radiance within 1e-3 on {frac:.6f} of pixels"
         assert rmse_over_mean_luminance(img, ref) < 0.05
     o.close()
+
+
+def tile_sequence(n_samples, ntx, nty, first_frame=2):
+    """(frame, tileX, tileY) of every Render() of TiledRenderer for n_samples samples: tileX runs fastest, tileY counts DOWN from
+    the top row, and `frame` advances with every tile step (TiledRenderer.cpp:55-64,485-501)."""
+    frame = first_frame
+    for _ in range(n_samples):
+        for ty in range(nty - 1, -1, -1):
+            for tx in range(ntx):
+                yield frame, tx, ty
+                frame += 1
+
+
+def test_tiled_render_vs_llvmpipe(golden_dir, oracle_lib):
+    """The reference run with tileWidth = tileHeight = 64 (16 tile steps per sample, a new `frame` for each): pins the tile
+    order, the tile uniforms of renderer.glsl:27-33 and the frame numbering the RNG is seeded with."""
+    g = np.load(os.path.join(golden_dir, "cornell_tiled_llvmpipe.npz"))
+    n, tile = int(g["nspp"]), int(g["tile"])
+    o = Oracle(_pack(golden_dir, "cornell"))
+    o.update_params(tile_width=tile, tile_height=tile)
+    acc = np.zeros((256, 256, 3), np.float32)
+    for frame, tx, ty in tile_sequence(n, 256 // tile, 256 // tile):
+        o.render_frames(frame, 1, 1, tx, ty, acc)
+    o.close()
+    img = acc / np.float32(n)
+    assert radiance_agreement(img, g["sppN"]) >= 0.999
+    assert rmse_over_mean_luminance(img, g["sppN"]) < 0.005
