@@ -2,13 +2,18 @@
 // load the scene with the reference's loader, construct the renderer, loop Update -> Render until
 // `maxSamples + 1 == GetSampleCount()` (Main.cpp:197), then fetch GetOutputBufferHDR.
 //
-//   lf_render <scene> --spp N [--out img.f32] [--device D] [--tonemap] [--megakernel]
-// img.f32: W*H*3 float32, rows bottom-up (the exporters flip, Export.h:19).
+//   lf_render <scene> --spp N [--out img.f32] [--png f.png] [--bmp f.bmp] [--tga f.tga] [--jpg f.jpg] [--device D] [--tonemap]
+// img.f32: W*H*3 float32, rows bottom-up (the exporters flip, Export.h:19).  --png / --bmp / --tga / --jpg do what SaveFrame,
+// SaveFrameBMP, SaveFrameTGA and SaveFrameJPG do (LavaFrame/Export.h:14-57): GetOutputBuffer -> stbi_flip_vertically_on_write ->
+// stbi_write_*, with the reference's own stb_image_write.h compiled from where it lies.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+
+#define STB_IMAGE_WRITE_IMPLEMENTATION
+#include "stb_image_write.h"
 
 #include "Scene.h"
 #include "Loader.h"
@@ -20,13 +25,17 @@ extern LavaFrameState GlobalState;
 
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: lf_render <scene> --spp N [--out img.f32] [--device D] [--tonemap]\n"); return 2; }
-    std::string out;
+    std::string out, png, bmp, tga, jpg;
     int spp = 1, device = 0;
     bool keepTonemap = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--spp") spp = atoi(argv[++i]);
         else if (a == "--out") out = argv[++i];
+        else if (a == "--png") png = argv[++i];
+        else if (a == "--bmp") bmp = argv[++i];
+        else if (a == "--tga") tga = argv[++i];
+        else if (a == "--jpg") jpg = argv[++i];
         else if (a == "--device") device = atoi(argv[++i]);
         else if (a == "--tonemap") keepTonemap = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -63,6 +72,17 @@ int main(int argc, char** argv) {
            "\"mean_rgb\": [%.8g, %.8g, %.8g]}\n", w, h, spp, steps, sec, (double)w * h * spp / sec, sum[0] / (w * h), sum[1] / (w * h), sum[2] / (w * h));
     if (!out.empty()) { FILE* f = fopen(out.c_str(), "wb"); fwrite(img, 4, (size_t)w * h * 3, f); fclose(f); }
     delete[] img;
+    if (!png.empty() || !bmp.empty() || !tga.empty() || !jpg.empty()) {   // Export.h:14-57
+        unsigned char* data = nullptr;
+        int ew = 0, eh = 0;
+        r->GetOutputBuffer(&data, ew, eh);
+        stbi_flip_vertically_on_write(true);
+        if (!png.empty()) stbi_write_png(png.c_str(), ew, eh, 3, data, ew * 3);
+        if (!bmp.empty()) stbi_write_bmp(bmp.c_str(), ew, eh, 3, data);
+        if (!tga.empty()) stbi_write_tga(tga.c_str(), ew, eh, 3, data);
+        if (!jpg.empty()) stbi_write_jpg(jpg.c_str(), ew, eh, 3, data, GlobalState.currentJpgQuality);
+        delete[] data;
+    }
     delete r;
     return 0;
 }

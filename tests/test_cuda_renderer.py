@@ -143,11 +143,18 @@ def test_headless_cxx_driver(golden_dir, gpu, tmp_path):
     n = int(g["nspp"])
     scene = gen_scenes.cornell_256(str(tmp_path / "cornell"))
     out = str(tmp_path / "img.f32")
-    res = subprocess.run([exe, scene, "--spp", str(n), "--out", out], check=True, capture_output=True, text=True, timeout=300)
+    png, bmp = str(tmp_path / "img.png"), str(tmp_path / "img.bmp")
+    res = subprocess.run([exe, scene, "--spp", str(n), "--out", out, "--png", png, "--bmp", bmp], check=True, capture_output=True, text=True, timeout=300)
     info = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert (info["width"], info["height"], info["spp"], info["tile_steps"]) == (256, 256, n, n)
     img = np.fromfile(out, np.float32).reshape(256, 256, 3)
     assert radiance_agreement(img, g["sppN"]) >= 0.99
+    # SaveFrame / SaveFrameBMP (Export.h:14-57): GetOutputBuffer's 8-bit image, flipped to top row first
+    from PIL import Image
+    want = np.rint(np.clip(img, 0, 1) * 255).astype(np.uint8)[::-1]
+    for f in (png, bmp):
+        got = np.asarray(Image.open(f).convert("RGB"))
+        assert got.shape == (256, 256, 3) and np.array_equal(got, want), f
     # the same scene with 64x64 tiles: 16 tile steps per sample and a new `frame` (RNG seed) for every tile step, against the
     # reference's own tiled run on llvmpipe
     gt = np.load(os.path.join(golden_dir, "cornell_tiled_llvmpipe.npz"))
