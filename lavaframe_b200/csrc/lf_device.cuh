@@ -3,8 +3,8 @@
 // environment sampling.  Each function cites the GLSL it implements (paths under /root/reference/shaders/).
 //
 // Arithmetic contract: IEEE fp32, compiled with -fmad=false so that no multiply-add is contracted (the
-// reference GLSL on llvmpipe does not contract either); divisions and square roots are the correctly rounded
-// ones.  Operation ORDER follows the GLSL expression trees, because the parity bar (1e-3 per pixel on 99.9 %
+// reference GLSL on llvmpipe does not contract either); square roots and reciprocals are the correctly rounded
+// ones, and a GLSL division x / y is x * (1 / y) (fdiv below) because that is what Mesa's compiler emits.  Operation ORDER follows the GLSL expression trees, because the parity bar (1e-3 per pixel on 99.9 %
 // of pixels with a seeded RNG) needs identical branch decisions almost everywhere.
 #pragma once
 
@@ -31,10 +31,12 @@ LFD f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 LFD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
 LFD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 LFD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
-LFD f3 operator/(f3 a, f3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+// GLSL x / y as Mesa lowers it (MUL by RCP; two roundings).  Pinned against llvmpipe by the oracle's golden tests.
+LFD float fdiv(float a, float b) { return a * (1.0f / b); }
+LFD f3 operator/(f3 a, f3 b) { return mk3(fdiv(a.x, b.x), fdiv(a.y, b.y), fdiv(a.z, b.z)); }
 LFD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 LFD f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
-LFD f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+LFD f3 operator/(f3 a, float s) { float r = 1.0f / s; return mk3(a.x * r, a.y * r, a.z * r); }
 LFD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 LFD float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 LFD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
@@ -43,12 +45,12 @@ LFD float length(f3 v) { return sqrtf(dot(v, v)); }
 LFD float gmax(float a, float b) { return a > b ? a : b; }          // MAXPS(a, b) operand semantics
 LFD float gmin(float a, float b) { return a < b ? a : b; }
 LFD float clampf(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
-LFD float mixf(float a, float b, float t) { return a + (b - a) * t; }
+LFD float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }   // mix() as Mesa lowers it for llvmpipe
 LFD f3 mix3(f3 a, f3 b, float t) { return mk3(mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t)); }
 LFD f3 reflect3(f3 I, f3 N) { return I - (2.0f * dot(N, I)) * N; }
 LFD f3 refract3(f3 I, f3 N, float eta) {
     float ndi = dot(N, I);
-    float k = 1.0f - eta * eta * (1.0f - ndi * ndi);
+    float k = 1.0f - eta * (eta * (1.0f - ndi * ndi));   // Mesa's builtin: mul(eta, mul(eta, ...))
     if (k < 0.0f) return mk3(0.0f);
     return eta * I - (eta * ndi + sqrtf(k)) * N;
 }
@@ -67,12 +69,16 @@ LFD float4 ldg4(const float4* p) { return __ldg(p); }
 // 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100+): a 64-byte node costs 2 L1 lookups per lane instead of 4.
 // Used for the nodes only: on the 48-byte triangle records (256 + 128 bit) it measured slower than 3 x LDG.E.128.
 struct f8 { float4 lo, hi; };
+#ifdef LF_HOST_CHECK   // tests/hostcheck compiles this header for the host: no PTX there
+LFD f8 ldg8(const float4* p) { f8 r; r.lo = p[0]; r.hi = p[1]; return r; }
+#else
 LFD f8 ldg8(const float4* p) {
     f8 r;
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
     return r;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------- RNG
 // globals.glsl:122-133.  State lives in registers inside a kernel, in PathSoA::rng between kernels.
@@ -127,7 +133,7 @@ LFD float SphereIntersect(float rad, f3 pos, const Ray& r) {   // intersection.g
 }
 LFD float RectIntersect(f3 pos, f3 u, f3 v, f3 n, float planeW, const Ray& r) {   // intersection.glsl:30-50
     float dt = dot(r.d, n);
-    float t = (planeW - dot(n, r.o)) / dt;
+    float t = fdiv(planeW - dot(n, r.o), dt);
     if (t > kEPS) {
         f3 p = r.o + r.d * t;
         f3 vi = p - pos;
@@ -198,7 +204,7 @@ LFD bool test_lights(const DevScene& S, const Ray& r, float maxDist, Hit& hit, D
                 if (d < hit.t) {
                     hit.t = d;
                     float cosTheta = dot(-r.d, L.normal);
-                    hit.lpdf = (d * d) / (L.area * cosTheta);
+                    hit.lpdf = fdiv(d * d, L.area * cosTheta);
                     hit.light = i;
                 }
             }
@@ -208,7 +214,7 @@ LFD bool test_lights(const DevScene& S, const Ray& r, float maxDist, Hit& hit, D
             if (ANY) { if (d > 0.0f && d < maxDist) return true; }
             else {
                 if (d < 0.f) d = kINF;
-                if (d < hit.t) { hit.t = d; hit.lpdf = (d * d) / L.area; hit.light = i; }
+                if (d < hit.t) { hit.t = d; hit.lpdf = fdiv(d * d, L.area); hit.light = i; }
             }
         }
     }
@@ -311,11 +317,12 @@ LFD bool walk_leaf(const DevScene& S, const Walk& w, float maxDist, Hit& hit, De
         if (b * det < 0.f) continue;
         float c = dot(e1, qv);
         if (c * det < 0.f) continue;
-        float uu = a / det;
-        float vv = b / det;
+        float rdet = 1.0f / det;                  // uvt.xyz / det = uvt.xyz * rcp(det)
+        float uu = a * rdet;
+        float vv = b * rdet;
         float ww = 1.0f - uu - vv;
         if (!(uu >= 0.f) || !(vv >= 0.f) || !(ww >= 0.f)) continue;
-        float tt = c / det;
+        float tt = c * rdet;
         if (!(tt >= 0.f)) continue;
         if (ANY) { if (tt < maxDist) return true; }
         else if (tt < hit.t) { hit.t = tt; hit.u = uu; hit.v = vv; hit.tri = first + i; hit.inst = w.curInst; hit.mat = w.curMat; hit.light = -1; }
@@ -368,7 +375,7 @@ LFD f3 ImportanceSampleGTR1(float rgh, float r1) {   // sampling.glsl:7-21
     float a = gmax(0.001f, rgh);
     float a2 = a * a;
     float phi = r1 * kTWO_PI;
-    float cosTheta = sqrtf((1.0f - lf_pow(a2, 1.0f - r1)) / (1.0f - a2));
+    float cosTheta = sqrtf(fdiv(1.0f - lf_pow(a2, 1.0f - r1), 1.0f - a2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi;
     lf_sincos(phi, sinPhi, cosPhi);
@@ -377,7 +384,7 @@ LFD f3 ImportanceSampleGTR1(float rgh, float r1) {   // sampling.glsl:7-21
 LFD f3 ImportanceSampleGTR2(float rgh, float r1, float r2) {   // sampling.glsl:37-49
     float a = gmax(0.001f, rgh);
     float phi = r1 * kTWO_PI;
-    float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
+    float cosTheta = sqrtf(fdiv(1.0f - r2, 1.0f + (a * a - 1.0f) * r2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi;
     lf_sincos(phi, sinPhi, cosPhi);
@@ -392,20 +399,20 @@ LFD float DielectricFresnel(float cos_theta_i, float eta) {   // sampling.glsl:6
     float sinThetaTSq = eta * eta * (1.0f - cos_theta_i * cos_theta_i);
     if (sinThetaTSq > 1.0f) return 1.0f;
     float cos_theta_t = sqrtf(gmax(1.0f - sinThetaTSq, 0.0f));
-    float rs = (eta * cos_theta_t - cos_theta_i) / (eta * cos_theta_t + cos_theta_i);
-    float rp = (eta * cos_theta_i - cos_theta_t) / (eta * cos_theta_i + cos_theta_t);
+    float rs = fdiv(eta * cos_theta_t - cos_theta_i, eta * cos_theta_t + cos_theta_i);
+    float rp = fdiv(eta * cos_theta_i - cos_theta_t, eta * cos_theta_i + cos_theta_t);
     return 0.5f * (rs * rs + rp * rp);
 }
 LFD float GTR1(float NDotH, float a) {   // sampling.glsl:79-87
     if (a >= 1.0f) return (1.0f / kPI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (kPI * lf_log(a2) * t);
+    return fdiv(a2 - 1.0f, kPI * lf_log(a2) * t);
 }
 LFD float GTR2(float NDotH, float a) {   // sampling.glsl:90-96
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return a2 / (kPI * t * t);
+    return fdiv(a2, kPI * t * t);
 }
 LFD float SmithG_GGX(float NDotV, float alphaG) {   // sampling.glsl:110-116
     float a = alphaG * alphaG;
@@ -433,7 +440,7 @@ LFD f3 UniformSampleSphere(float r1, float r2) {   // sampling.glsl:153-160
 }
 LFD float powerHeuristic(float a, float b) {   // sampling.glsl:163-169
     float t = a * a;
-    return t / (b * b + t);
+    return fdiv(t, b * b + t);
 }
 
 struct LightSample { f3 normal, emission, direction; float dist, pdf; };   // LightSampleRec, globals.glsl:99-106
@@ -453,7 +460,7 @@ LFD void sampleOneLight(const LightRec& light, int numLights, f3 surfacePos, Rng
         if (type == 0) rec.normal = normalize(cross(light.u, light.v));
         else rec.normal = normalize(lightSurfacePos - light.position);
         rec.emission = light.emission * (float)numLights;
-        rec.pdf = distSq / (light.area * fabsf(dot(rec.normal, rec.direction)));
+        rec.pdf = fdiv(distSq, light.area * fabsf(dot(rec.normal, rec.direction)));
     } else {
         rec.direction = normalize(light.position - mk3(0.0f));
         rec.normal = normalize(surfacePos - light.position);
@@ -489,7 +496,7 @@ LFN float EnvPdf(const DevScene& S, const DevParams& P, f3 dir) {   // sampling.
     float pdf = conditionalAt(S, ux, uy).y * marginalAt(S, uy).y;
     float st, ct;
     lf_sincos(theta, st, ct);
-    return (pdf * P.hdr_resolution) / (2.0f * kPI * kPI * st);
+    return fdiv(pdf * P.hdr_resolution, 2.0f * kPI * kPI * st);
 }
 // sampling.glsl:246-265; returns direction, pdf in .w
 LFN float4 EnvSample(const DevScene& S, const DevParams& P, Rng& rng, f3& color) {
@@ -504,26 +511,27 @@ LFN float4 EnvSample(const DevScene& S, const DevParams& P, Rng& rng, f3& color)
     lf_sincos(theta, st, ct);
     lf_sincos(phi, sph, cph);
     if (st == 0.0f) pdf = 0.0f;
-    return make_float4(-st * cph, ct, -st * sph, (pdf * P.hdr_resolution) / (2.0f * kPI * kPI * st));
+    return make_float4(-st * cph, ct, -st * sph, fdiv(pdf * P.hdr_resolution, 2.0f * kPI * kPI * st));
 }
 
-// material texture array: RGBA8, LINEAR, REPEAT; fetched unfiltered and lerped in fp32 (Renderer.cpp:151-160)
+// material texture array: RGBA8, LINEAR, REPEAT (Renderer.cpp:151-160), fetched unfiltered and filtered the way llvmpipe
+// filters 8-bit formats: texel coordinates in 24.8 fixed point, X = round_to_nearest_even(u * W * 256) - 128, texels
+// X >> 8 and its +1 neighbour (wrapped), weight X & 255; each lerp is v0 + ((w * (v1 - v0)) >> 8) on the 8-bit channel
+// values (x first, then y); the 8-bit result times the float constant 1/255.  (The hardware filter, 9-bit weights on
+// normalised floats, would not reproduce it.)
+LFD int lerp8(int w, int v0, int v1) { return (v0 + ((w * (v1 - v0)) >> 8)) & 255; }
 template <bool COUNT>
 LFN float4 texArrayLinear(const DevScene& S, float u, float v, int layer, DevCounters* cnt) {
     layer = max(0, min(layer, S.num_tex - 1));
     bump<COUNT>(cnt, C_TEX);
-    float x = u * (float)S.tex_w - 0.5f, y = v * (float)S.tex_h - 0.5f;
-    float fx = floorf(x), fy = floorf(y);
-    float wx = x - fx, wy = y - fy;
-    int x0 = wrapi((int)fx, S.tex_w), x1 = wrapi((int)fx + 1, S.tex_w), y0 = wrapi((int)fy, S.tex_h), y1 = wrapi((int)fy + 1, S.tex_h);
+    int X = __float2int_rn(u * (float)S.tex_w * 256.0f) - 128, Y = __float2int_rn(v * (float)S.tex_h * 256.0f) - 128;
+    int wx = X & 255, wy = Y & 255;
+    int x0 = wrapi(X >> 8, S.tex_w), x1 = wrapi((X >> 8) + 1, S.tex_w), y0 = wrapi(Y >> 8, S.tex_h), y1 = wrapi((Y >> 8) + 1, S.tex_h);
     uchar4 a = tex2DLayered<uchar4>(S.tex_maps, (float)x0, (float)y0, layer), b = tex2DLayered<uchar4>(S.tex_maps, (float)x1, (float)y0, layer);
     uchar4 c = tex2DLayered<uchar4>(S.tex_maps, (float)x0, (float)y1, layer), e = tex2DLayered<uchar4>(S.tex_maps, (float)x1, (float)y1, layer);
-    auto cv = [](uchar4 q) { return make_float4(q.x / 255.0f, q.y / 255.0f, q.z / 255.0f, q.w / 255.0f); };
-    float4 A = cv(a), B = cv(b), C = cv(c), E = cv(e);
-    auto L = [](float p, float q, float w) { return p + (q - p) * w; };
-    float4 top = make_float4(L(A.x, B.x, wx), L(A.y, B.y, wx), L(A.z, B.z, wx), L(A.w, B.w, wx));
-    float4 bot = make_float4(L(C.x, E.x, wx), L(C.y, E.y, wx), L(C.z, E.z, wx), L(C.w, E.w, wx));
-    return make_float4(L(top.x, bot.x, wy), L(top.y, bot.y, wy), L(top.z, bot.z, wy), L(top.w, bot.w, wy));
+    const float k = (float)(1.0 / 255.0);
+    return make_float4((float)lerp8(wy, lerp8(wx, a.x, b.x), lerp8(wx, c.x, e.x)) * k, (float)lerp8(wy, lerp8(wx, a.y, b.y), lerp8(wx, c.y, e.y)) * k,
+                       (float)lerp8(wy, lerp8(wx, a.z, b.z), lerp8(wx, c.z, e.z)) * k, (float)lerp8(wy, lerp8(wx, a.w, b.w), lerp8(wx, c.w, e.w)) * k);
 }
 
 // ---------------------------------------------------------------------------------------------- disney.glsl
@@ -532,7 +540,7 @@ LFN f3 EvalDielectricReflection(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pd
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     float F = DielectricFresnel(dot(V, H), s.eta);
     float D = GTR2(dot(N, H), s.mat.roughness);
-    pdf = D * dot(N, H) * F / (4.0f * fabsf(dot(V, H)));
+    pdf = fdiv(D * dot(N, H) * F, 4.0f * fabsf(dot(V, H)));
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return s.mat.albedo * F * D * G;
 }
@@ -542,7 +550,7 @@ LFN f3 EvalDielectricRefraction(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pd
     float F = DielectricFresnel(fabsf(dot(V, H)), s.eta);
     float D = GTR2(dot(N, H), s.mat.roughness);
     float denomSqrt = dot(L, H) + dot(V, H) * s.eta;
-    pdf = D * dot(N, H) * (1.0f - F) * fabsf(dot(L, H)) / (denomSqrt * denomSqrt);
+    pdf = fdiv(D * dot(N, H) * (1.0f - F) * fabsf(dot(L, H)), denomSqrt * denomSqrt);
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return s.mat.albedo * (1.0f - F) * D * G * fabsf(dot(V, H)) * fabsf(dot(L, H)) * 4.0f * s.eta * s.eta / (denomSqrt * denomSqrt);
 }
@@ -550,7 +558,7 @@ LFN f3 EvalSpecular(const Surf& s, f3 Cspec0, f3 V, f3 N, f3 L, f3 H, float& pdf
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     float D = GTR2(dot(N, H), s.mat.roughness);
-    pdf = D * dot(N, H) / (4.0f * dot(V, H));
+    pdf = fdiv(D * dot(N, H), 4.0f * dot(V, H));
     float FH = SchlickFresnel(dot(L, H));
     f3 F = mix3(Cspec0, mk3(1.0f), FH);
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
@@ -560,7 +568,7 @@ LFN f3 EvalClearcoat(const Surf& s, f3 V, f3 N, f3 L, f3 H, float& pdf) {   // d
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return mk3(0.0f);
     float D = GTR1(dot(N, H), mixf(0.1f, 0.001f, s.mat.clearcoatRoughness));
-    pdf = D * dot(N, H) / (4.0f * dot(V, H));
+    pdf = fdiv(D * dot(N, H), 4.0f * dot(V, H));
     float FH = SchlickFresnel(dot(L, H));
     float F = mixf(0.04f, 1.0f, FH);
     float G = SmithG_GGX(dot(N, L), 0.25f) * SmithG_GGX(dot(N, V), 0.25f);
@@ -745,7 +753,7 @@ LFD void load_surface(const DevScene& S, const Hit& hit, f3 rdir, Surf& s, DevCo
 
 // renderer.glsl:20-62: pixel mapping, RNG seed, tent jitter, thin-lens camera ray for tile-local pixel (lx, ly).
 LFD float mapf(float value, float low1, float high1, float low2, float high2) {
-    return low2 + ((value - low1) * (high2 - low2)) / (high1 - low1);
+    return low2 + fdiv((value - low1) * (high2 - low2), high1 - low1);
 }
 LFD Ray camera_ray(const DevParams& P, int lx, int ly, int frame, Rng& rng) {
     float resx = (float)P.width, resy = (float)P.height;
@@ -763,10 +771,10 @@ LFD Ray camera_ray(const DevParams& P, int lx, int ly, int frame, Rng& rng) {
     float r2 = 2.0f * rnd(rng);
     float jx = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
     float jy = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
-    jx = jx / (resx * 0.5f);
-    jy = jy / (resy * 0.5f);
+    jx = fdiv(jx, resx * 0.5f);
+    jy = fdiv(jy, resy * 0.5f);
     float dx = ctx + jx, dy = cty + jy;
-    dy *= resy / resx * P.cam_scale;
+    dy *= fdiv(resy, resx) * P.cam_scale;
     dx *= P.cam_scale;
     f3 right = mk3(P.cam_right[0], P.cam_right[1], P.cam_right[2]), up = mk3(P.cam_up[0], P.cam_up[1], P.cam_up[2]);
     f3 fwd = mk3(P.cam_fwd[0], P.cam_fwd[1], P.cam_fwd[2]), pos = mk3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
@@ -793,10 +801,10 @@ LFD Ray preview_ray(const DevParams& P, int x, int y, Rng& rng) {
     float r2 = 2.0f * rnd(rng);
     float jx = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
     float jy = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
-    jx = jx / resx;
-    jy = jy / resy;
+    jx = fdiv(jx, resx);
+    jy = fdiv(jy, resy);
     float dx = (2.0f * tcx - 1.0f) + jx, dy = (2.0f * tcy - 1.0f) + jy;
-    dy *= resy / resx * P.cam_scale;
+    dy *= fdiv(resy, resx) * P.cam_scale;
     dx *= P.cam_scale;
     f3 right = mk3(P.cam_right[0], P.cam_right[1], P.cam_right[2]), up = mk3(P.cam_up[0], P.cam_up[1], P.cam_up[2]);
     f3 fwd = mk3(P.cam_fwd[0], P.cam_fwd[1], P.cam_fwd[2]), pos = mk3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);

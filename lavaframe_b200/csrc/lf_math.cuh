@@ -1,17 +1,16 @@
 // lf_math.cuh — transcendental functions of the path tracer, written out in plain fp32 arithmetic.
 //
-// GLSL leaves the precision of sin/cos/pow/exp/log/acos/atan to the implementation (the only runnable reference,
-// llvmpipe, evaluates them with its own polynomials), so any accurate implementation is as faithful as another.  These
-// use the classic Cephes single-precision kernels (Cody-Waite range reduction + minimax polynomials) restricted to
-// + - * / sqrt, floor and bit operations, with every operation separately rounded (the file is compiled -fmad=false).
-// Two consequences:
-//   * results are bit-reproducible on any IEEE machine: the CPU oracle restates the same formulas and the parity tests
-//     compare radiance bit for bit, instead of drowning in last-ulp differences between libm implementations that
+// GLSL leaves the precision of sin/cos/tan/pow/exp/log/acos/atan to the implementation, and the only runnable reference
+// implementation is Mesa llvmpipe (the tier-1 oracle), so these functions restate ITS evaluation: Cephes-style sincos,
+// gallivm's exp2 / log2 polynomials, Mesa's GLSL-level expansions of acos / atan.  They use only + - * / sqrt, floor and
+// bit operations, every operation separately rounded (the file is compiled -fmad=false), so:
+//   * results are bit-reproducible on any IEEE machine: the CPU oracle states the same formulas (oracle/lf_math_oracle.h)
+//     and is itself pinned bit for bit against llvmpipe executing the GLSL built-ins (tests/golden/llvmpipe_builtins.npz),
+//     so CUDA, oracle and the reference on llvmpipe agree bit for bit instead of drowning in last-ulp differences that
 //     glass and metal chains amplify;
 //   * the code is a fraction of the CUDA math library's (no Payne-Hanek paths), which matters because the shade kernel
 //     was instruction-cache bound (156 KB of SASS, `no_instruction` the top stall; profiles/README.md).
-// Accuracy: <= 2 ulp for sin/cos on |x| < 8192, <= 1-2 ulp for exp/log, ~1e-6 relative for pow (exp(y log x)),
-// <= 2 ulp for acos/atan2.  Arguments on the path are bounded: angles in [0, 2 pi], cosines in [-1, 1], colours in [0, 1].
+// Arguments on the path are bounded: angles in [0, 2 pi], cosines in [-1, 1], colours in [0, 1].
 #pragma once
 
 #include <cuda_runtime.h>
@@ -44,82 +43,81 @@ LFM void lf_sincos(float x, float& s, float& c) {
     c = cv;
 }
 
-// 2^n as a float for n in [-126, 127]
-__device__ __forceinline__ float lf_pow2i(int n) { return __int_as_float((n + 127) << 23); }
+// tan(x) = sin(x) * (1 / cos(x)): Mesa lowers tan to sin / cos and every division to a multiplication by the reciprocal
+LFM float lf_tan(float x) { float s, c; lf_sincos(x, s, c); return s * (1.0f / c); }
 
-// Cephes expf; exact 0 below 2^-126 (no denormal results), +inf above the fp32 range
-LFM float lf_exp(float x) {
-    if (!(x <= 88.72283905206835f)) return (x != x) ? x : __int_as_float(0x7f800000);
-    if (x < -87.33654475055310898657f) return 0.0f;
-    float z = floorf(1.44269504088896341f * x + 0.5f);
-    int n = (int)z;
-    x = (x - z * 0.693359375f) - z * -2.12194440e-4f;
-    float xx = x * x;
-    float p = (((((1.9875691500E-4f * x + 1.3981999507E-3f) * x + 8.3334519073E-3f) * x + 4.1665795894E-2f) * x + 1.6666665459E-1f) * x
-               + 5.0000001201E-1f) * xx + x + 1.0f;
-    if (n > 127) return p * lf_pow2i(127) * lf_pow2i(n - 127);
-    if (n < -126) return 0.0f;
-    return p * lf_pow2i(n);
+// ---- exp / log / pow / acos / atan exactly as llvmpipe evaluates the GLSL built-ins.  Mesa's GLSL front end rewrites
+// exp(x) = exp2(x * log2 e) and log(x) = log2(x) * ln 2; pow stays one instruction that gallivm evaluates as
+// exp2(log2(x) * y); acos / atan(y, x) are expanded into the polynomial expressions of Mesa's builtin_functions.cpp.
+// gallivm's exp2 / log2 are minimax polynomials of degree 5 / 4 evaluated in even / odd halves, no contraction.
+__device__ __forceinline__ float lf_mad(float a, float b, float c) { return a * b + c; }   // -fmad=false: two roundings
+
+// exp2: clamp to [-126.99999, 128], 2^floor(x) from exponent bits, polynomial in fract(x)
+__device__ __forceinline__ float lf_exp2(float x) {
+    x = (128.0f < x) ? 128.0f : x;
+    x = (-126.99999f > x) ? -126.99999f : x;
+    float ip = floorf(x);
+    float fp = x - ip;
+    float e = __int_as_float(((int)ip + 127) << 23);
+    float f2 = fp * fp;
+    float even = lf_mad(f2, lf_mad(f2, 0.00898934009049466391101f, 0.240153617044375388211f), 1.0f);
+    float odd = lf_mad(f2, lf_mad(f2, 0.00187757667519147912699f, 0.0558263180532956664775f), 0.693153073200168932794f);
+    return e * lf_mad(odd, fp, even);
 }
-
-// Cephes logf; log(0) = -inf, log(x < 0) = NaN, denormals are scaled up first
+// log2 without edge cases (pow's): exponent + y P(y^2), y = (m - 1) / (m + 1); the sign bit is ignored
+__device__ __forceinline__ float lf_log2_raw(float x) {
+    int i = __float_as_int(x);
+    float logexp = (float)(((i & 0x7f800000) >> 23) - 127);
+    float mant = __int_as_float((i & 0x007fffff) | 0x3f800000);
+    float y = (mant - 1.0f) / (mant + 1.0f);
+    float z = y * y;
+    float z2 = z * z;
+    float even = lf_mad(z2, lf_mad(z2, 0.406718052498846252698f, 0.577440339438736392009f), 2.88539009343309178325f);
+    float odd = lf_mad(z2, 0.403343858251329912514f, 0.961791550404184197881f);
+    return lf_mad(y, lf_mad(odd, z, even), logexp);
+}
+LFM float lf_exp(float x) { return lf_exp2(x * 1.44269504088896340736f); }
+// log(x) = log2(x) * ln 2 with the LG2 instruction's edge cases: +inf, 0 -> -inf, negative or NaN -> NaN
 LFM float lf_log(float x) {
-    if (!(x > 0.0f)) return (x == 0.0f) ? __int_as_float(0xff800000) : __int_as_float(0x7fc00000);
-    if (x == __int_as_float(0x7f800000)) return x;
-    int e = 0;
-    if (x < 1.17549435e-38f) { x = x * 8388608.0f; e = -23; }
-    int bits = __float_as_int(x);
-    e += ((bits >> 23) & 0xff) - 126;
-    float m = __int_as_float((bits & 0x007fffff) | 0x3f000000);   // mantissa in [0.5, 1)
-    if (m < 0.707106781186547524f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
-    float z = m * m;
-    float y = ((((((((7.0376836292E-2f * m - 1.1514610310E-1f) * m + 1.1676998740E-1f) * m - 1.2420140846E-1f) * m + 1.4249322787E-1f) * m
-                  - 1.6668057665E-1f) * m + 2.0000714765E-1f) * m - 2.4999993993E-1f) * m + 3.3333331174E-1f) * m * z;
-    float fe = (float)e;
-    y = y + -2.12194440e-4f * fe;
-    y = y - 0.5f * z;
-    return (m + y) + 0.693359375f * fe;
+    float r = lf_log2_raw(x);
+    if (x >= __int_as_float(0x7f800000)) r = __int_as_float(0x7f800000);
+    if (x == 0.0f) r = __int_as_float(0xff800000);
+    if (!(x >= 0.0f)) r = __int_as_float(0x7fc00000);
+    return r * 0.693147180559945309417f;
 }
+LFM float lf_pow(float x, float y) { return lf_exp2(lf_log2_raw(x) * y); }
 
-// pow for the path's uses (x >= 0): exp(y * log(x)); pow(0, y > 0) = 0
-LFM float lf_pow(float x, float y) {
-    if (x == 0.0f) return (y > 0.0f) ? 0.0f : ((y == 0.0f) ? 1.0f : __int_as_float(0x7f800000));
-    return lf_exp(y * lf_log(x));
-}
-
-// Cephes asinf kernel on [0, 0.5]
-__device__ __forceinline__ float lf_asin_poly(float a) {
-    float z = a * a;
-    return ((((4.2163199048E-2f * z + 2.4181311049E-2f) * z + 4.5470025998E-2f) * z + 7.4953002686E-2f) * z + 1.6666752422E-1f) * z * a + a;
-}
-// acos with the argument clamped to [-1, 1] (the shader's unclamped acos of a unit vector's y can be an ulp outside)
+__device__ __forceinline__ float lf_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+// acos(x) = pi/2 - sign(x) * (pi/2 - sqrt(1 - |x|) * (pi/2 + |x| * (pi/4 - 1 + |x| * (0.08132463 + |x| * -0.02363318))))
 LFM float lf_acos(float x) {
-    if (x != x) return x;
-    if (x > 1.0f) x = 1.0f;
-    if (x < -1.0f) x = -1.0f;
-    float a = fabsf(x);
-    if (a <= 0.5f) return 1.57079632679489661923f - ((x < 0.0f) ? -lf_asin_poly(a) : lf_asin_poly(a));
-    float t = 2.0f * lf_asin_poly(sqrtf(0.5f * (1.0f - a)));
-    return (x > 0.0f) ? t : 3.14159265358979323846f - t;
+    const float PIO2_F = 1.57079632679489661923f;
+    float ax = fabsf(x);
+    float as = lf_sign(x) * (PIO2_F - sqrtf(1.0f - ax) * (PIO2_F + ax * ((0.785398163397448309616f - 1.0f) + ax * (0.08132463f + ax * -0.02363318f))));
+    return PIO2_F - as;
 }
-
-// Cephes atanf kernel for t >= 0
-__device__ __forceinline__ float lf_atan_pos(float t) {
-    float y0;
-    if (t > 2.414213562373095f) { y0 = 1.57079632679489661923f; t = -(1.0f / t); }
-    else if (t > 0.4142135623730950f) { y0 = 0.785398163397448309616f; t = (t - 1.0f) / (t + 1.0f); }
-    else y0 = 0.0f;
-    float z = t * t;
-    return y0 + ((((8.05374449538e-2f * z - 1.38776856032E-1f) * z + 1.99777106478E-1f) * z - 3.33329491539E-1f) * z * t + t);
+// Mesa's do_atan for an argument >= 0
+__device__ __forceinline__ float lf_atan_pos(float a) {
+    float mn = a < 1.0f ? a : 1.0f, mx = a > 1.0f ? a : 1.0f;
+    float x = mn * (1.0f / mx);
+    float t = x * x;
+    float r = ((((((((((-0.0121323213173444f * t) + 0.0536813784310406f) * t) - 0.1173503194786851f) * t) + 0.1938924977115610f) * t) - 0.3326756418091246f) * t)
+               + 0.9999793128310355f) * x;
+    r = r + (a > 1.0f ? 1.0f : 0.0f) * (r * -2.0f + 1.57079632679489661923f);
+    return r * lf_sign(a);
 }
-// atan(y, x) of GLSL: angle of (x, y) in (-pi, pi]
+// atan(y, x) of GLSL as Mesa's _atan2 expands it
 LFM float lf_atan2(float y, float x) {
-    if (x != x || y != y) return __int_as_float(0x7fc00000);
-    const float PI_F = 3.14159265358979323846f, PIO2_F = 1.57079632679489661923f;
-    if (x == 0.0f) return (y > 0.0f) ? PIO2_F : ((y < 0.0f) ? -PIO2_F : 0.0f);
-    float a = lf_atan_pos(fabsf(y / x));
-    if (x < 0.0f) a = PI_F - a;
-    return (y < 0.0f) ? -a : a;
+    bool flip = 0.0f >= x;
+    float s = flip ? fabsf(x) : y;
+    float t = flip ? y : fabsf(x);
+    float scale = (fabsf(t) >= 1e18f) ? 0.25f : 1.0f;
+    float rcp = 1.0f / (t * scale);
+    float sot = (s * scale) * rcp;
+    float tn = (fabsf(x) == fabsf(y)) ? 1.0f : fabsf(sot);
+    float arc = lf_atan_pos(tn);
+    arc = arc + (flip ? 1.0f : 0.0f) * 1.57079632679489661923f;
+    float m = y < rcp ? y : rcp;
+    return (m < 0.0f) ? -arc : arc;
 }
 
 }  // namespace lf

@@ -179,6 +179,27 @@ int alloc_state(lfcuda_ctx* ctx) {
     return 0;
 }
 
+// tan() of the reference shader as llvmpipe evaluates it: sin(x) * (1 / cos(x)) with the octant-reduced polynomial sincos of
+// lf_math.cuh, restated for the host (this file is compiled with -ffp-contract=off).  The kernels read the result as
+// DevParams::cam_scale; evaluating it once here instead of once per sample changes nothing in the arithmetic.
+static float glsl_tan(float x) {
+    float ax = std::fabs(x);
+    int j = (int)(ax * 1.27323954473516f);
+    j += (j & 1);
+    float y = (float)j;
+    float r = ((ax - y * 0.78515625f) - y * 2.4187564849853515625e-4f) - y * 3.77489497744594108e-8f;
+    float z = r * r;
+    float ps = ((-1.9515295891E-4f * z + 8.3321608736E-3f) * z - 1.6666654611E-1f) * z * r + r;
+    float pc = ((2.443315711809948E-005f * z - 1.388731625493765E-003f) * z + 4.166664568298827E-002f) * z * z - 0.5f * z + 1.0f;
+    int q = j & 7;
+    bool swap = (q == 2) || (q == 6);
+    float sv = swap ? pc : ps, cv = swap ? ps : pc;
+    if (q == 4 || q == 6) sv = -sv;
+    if (q == 2 || q == 4) cv = -cv;
+    if (x < 0.0f) sv = -sv;
+    return sv * (1.0f / cv);
+}
+
 void fill_dev_params(const lfcuda_ctx* c, DevParams& D, int first_frame, int nframes, int stride, int tile_x, int tile_y) {
     const LfParams& P = c->params;
     const LfCamera& C = c->camera;
@@ -195,7 +216,7 @@ void fill_dev_params(const lfcuda_ctx* c, DevParams& D, int first_frame, int nfr
     D.hdr_resolution = (float)(c->dev.hdr_w * c->dev.hdr_h);          // TiledRenderer.cpp:222
     D.inv_tiles_x = 1.0f / ((float)P.width / P.tile_width);            // TiledRenderer.cpp:226-227
     D.inv_tiles_y = 1.0f / ((float)P.height / P.tile_height);
-    D.cam_scale = tanf(C.fov * 0.5f);                                  // renderer.glsl:51
+    D.cam_scale = glsl_tan(C.fov * 0.5f);                              // renderer.glsl:51
     D.focal_dist = C.focal_dist; D.aperture = C.aperture;
     D.tile_x = tile_x; D.tile_y = tile_y;
     D.first_frame = first_frame; D.frame_stride = stride; D.num_frames = nframes;

@@ -1,12 +1,12 @@
 // lf_math_oracle.h — TEST INFRASTRUCTURE.  The oracle's sin/cos/exp/log/pow/acos/atan2.
 //
-// GLSL leaves the precision of these built-ins to the implementation (llvmpipe, the only runnable reference, uses its
-// own polynomials), so the oracle is free to pick any accurate evaluation.  It uses the classic Cephes single-precision
-// kernels written in plain fp32 (+ - * / sqrt floor, every operation separately rounded; this file is compiled with
-// -ffp-contract=off).  Such formulas give the same bits on any IEEE machine, which is what lets the parity tests compare
-// the CUDA kernels with this oracle bit for bit on glass/metal scenes, where libm-vs-libm last-ulp differences would
-// otherwise be amplified into different paths.  DESIGN.md lists the formulas; the CUDA side states them independently
-// in lavaframe_b200/csrc/lf_math.cuh.
+// GLSL leaves the precision of these built-ins to the implementation; the only runnable reference implementation is Mesa
+// llvmpipe (tier 1), so this file restates ITS evaluation: plain fp32 (+ - * / sqrt floor and bit operations, every
+// operation separately rounded; compiled with -ffp-contract=off), which gives the same bits on any IEEE machine.  Each
+// function below is pinned bit for bit against llvmpipe executing the GLSL built-in (oracle/_ref/lp_probe ->
+// tests/golden/llvmpipe_builtins.npz, tests/test_oracle_golden.py).  The CUDA side states the same formulas independently
+// in lavaframe_b200/csrc/lf_math.cuh, so CUDA, oracle and llvmpipe agree bit for bit on glass/metal chains that amplify
+// last-ulp differences into different paths.  Known residue: llvmpipe runs with denormals flushed to zero, this file does not.
 #pragma once
 
 #include <cmath>
@@ -38,75 +38,84 @@ static inline void sincos(float x, float& s, float& c) {
     c = cv;
 }
 
-static inline float pow2i(int n) { return bits2f((uint32_t)(n + 127) << 23); }
+// tan(x) = sin(x) * (1 / cos(x)) (Mesa lowers tan to sin / cos, and the division to a reciprocal)
+static inline float tan(float x) { float s, c; sincos(x, s, c); return s * (1.0f / c); }
 
-static inline float exp(float x) {
-    if (!(x <= 88.72283905206835f)) return (x != x) ? x : bits2f(0x7f800000u);
-    if (x < -87.33654475055310898657f) return 0.0f;
-    float z = std::floor(1.44269504088896341f * x + 0.5f);
-    int n = (int)z;
-    x = (x - z * 0.693359375f) - z * -2.12194440e-4f;
-    float xx = x * x;
-    float p = (((((1.9875691500E-4f * x + 1.3981999507E-3f) * x + 8.3334519073E-3f) * x + 4.1665795894E-2f) * x + 1.6666665459E-1f) * x
-               + 5.0000001201E-1f) * xx + x + 1.0f;
-    if (n > 127) return p * pow2i(127) * pow2i(n - 127);
-    if (n < -126) return 0.0f;
-    return p * pow2i(n);
-}
+// ---- exp / log / pow / acos / atan: the evaluation llvmpipe itself performs, pinned bit for bit with oracle/_ref/lp_probe
+// (tests/golden/llvmpipe_builtins.npz).  Mesa's GLSL front end rewrites exp(x) = exp2(x * log2 e), log(x) = log2(x) * ln 2,
+// x / y = x * (1 / y); pow stays one instruction that gallivm evaluates as exp2(log2(x) * y); acos / atan are expanded
+// into the polynomial expressions of Mesa's builtin_functions.cpp (asin_expr, do_atan, _atan2).  gallivm's exp2 / log2
+// (lp_bld_arit.c) are minimax polynomials of degree 5 / 4 evaluated in even / odd halves; llvmpipe's LLVM does not
+// contract the multiply-adds.
+static inline float mad(float a, float b, float c) { return a * b + c; }
 
-static inline float log(float x) {
-    if (!(x > 0.0f)) return (x == 0.0f) ? bits2f(0xff800000u) : bits2f(0x7fc00000u);
-    if (x == bits2f(0x7f800000u)) return x;
-    int e = 0;
-    if (x < 1.17549435e-38f) { x = x * 8388608.0f; e = -23; }
-    uint32_t b = f2bits(x);
-    e += (int)((b >> 23) & 0xff) - 126;
-    float m = bits2f((b & 0x007fffffu) | 0x3f000000u);
-    if (m < 0.707106781186547524f) { e -= 1; m = m + m - 1.0f; } else { m = m - 1.0f; }
-    float z = m * m;
-    float y = ((((((((7.0376836292E-2f * m - 1.1514610310E-1f) * m + 1.1676998740E-1f) * m - 1.2420140846E-1f) * m + 1.4249322787E-1f) * m
-                  - 1.6668057665E-1f) * m + 2.0000714765E-1f) * m - 2.4999993993E-1f) * m + 3.3333331174E-1f) * m * z;
-    float fe = (float)e;
-    y = y + -2.12194440e-4f * fe;
-    y = y - 0.5f * z;
-    return (m + y) + 0.693359375f * fe;
+// lp_build_exp2: clamp to [-126.99999, 128], 2^floor(x) by exponent bits, polynomial in fract(x)
+static inline float exp2(float x) {
+    x = (128.0f < x) ? 128.0f : x;
+    x = (-126.99999f > x) ? -126.99999f : x;
+    float ip = std::floor(x);
+    float fp = x - ip;
+    float e = bits2f((uint32_t)((int)ip + 127) << 23);
+    float f2 = fp * fp;
+    float even = mad(f2, mad(f2, 0.00898934009049466391101f, 0.240153617044375388211f), 1.0f);
+    float odd = mad(f2, mad(f2, 0.00187757667519147912699f, 0.0558263180532956664775f), 0.693153073200168932794f);
+    return e * mad(odd, fp, even);
 }
+// lp_build_log2_approx without the edge cases (what pow uses): exponent + y P(y^2), y = (m - 1) / (m + 1); the sign bit is ignored
+static inline float log2_raw(float x) {
+    uint32_t i = f2bits(x);
+    float logexp = (float)((int)((i & 0x7f800000u) >> 23) - 127);
+    float mant = bits2f((i & 0x007fffffu) | 0x3f800000u);
+    float y = (mant - 1.0f) / (mant + 1.0f);
+    float z = y * y;
+    float z2 = z * z;
+    float even = mad(z2, mad(z2, 0.406718052498846252698f, 0.577440339438736392009f), 2.88539009343309178325f);
+    float odd = mad(z2, 0.403343858251329912514f, 0.961791550404184197881f);
+    return mad(y, mad(odd, z, even), logexp);
+}
+// lp_build_log2_safe (the LG2 instruction): + inf, 0 and negative arguments
+static inline float log2(float x) {
+    float r = log2_raw(x);
+    if (x >= bits2f(0x7f800000u)) r = bits2f(0x7f800000u);
+    if (x == 0.0f) r = bits2f(0xff800000u);
+    if (!(x >= 0.0f)) r = bits2f(0x7fc00000u);   // negative or NaN
+    return r;
+}
+static inline float exp(float x) { return exp2(x * 1.44269504088896340736f); }
+static inline float log(float x) { return log2(x) * 0.693147180559945309417f; }
+static inline float pow(float x, float y) { return exp2(log2_raw(x) * y); }
 
-static inline float pow(float x, float y) {
-    if (x == 0.0f) return (y > 0.0f) ? 0.0f : ((y == 0.0f) ? 1.0f : bits2f(0x7f800000u));
-    return exp(y * log(x));
-}
-
-static inline float asin_poly(float a) {
-    float z = a * a;
-    return ((((4.2163199048E-2f * z + 2.4181311049E-2f) * z + 4.5470025998E-2f) * z + 7.4953002686E-2f) * z + 1.6666752422E-1f) * z * a + a;
-}
-// argument clamped to [-1, 1]
+static inline float sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+// acos(x) = pi/2 - asin_expr(x, 0.08132463, -0.02363318); NaN outside [-1, 1] (sqrt of a negative number)
 static inline float acos(float x) {
-    if (x != x) return x;
-    if (x > 1.0f) x = 1.0f;
-    if (x < -1.0f) x = -1.0f;
-    float a = std::fabs(x);
-    if (a <= 0.5f) return 1.57079632679489661923f - ((x < 0.0f) ? -asin_poly(a) : asin_poly(a));
-    float t = 2.0f * asin_poly(std::sqrt(0.5f * (1.0f - a)));
-    return (x > 0.0f) ? t : 3.14159265358979323846f - t;
+    const float PIO2_F = 1.57079632679489661923f;
+    float ax = std::fabs(x);
+    float as = sign(x) * (PIO2_F - std::sqrt(1.0f - ax) * (PIO2_F + ax * ((0.785398163397448309616f - 1.0f) + ax * (0.08132463f + ax * -0.02363318f))));
+    return PIO2_F - as;
 }
-
-static inline float atan_pos(float t) {
-    float y0;
-    if (t > 2.414213562373095f) { y0 = 1.57079632679489661923f; t = -(1.0f / t); }
-    else if (t > 0.4142135623730950f) { y0 = 0.785398163397448309616f; t = (t - 1.0f) / (t + 1.0f); }
-    else y0 = 0.0f;
-    float z = t * t;
-    return y0 + ((((8.05374449538e-2f * z - 1.38776856032E-1f) * z + 1.99777106478E-1f) * z - 3.33329491539E-1f) * z * t + t);
+// do_atan for an argument >= 0
+static inline float atan_pos(float a) {
+    float mn = a < 1.0f ? a : 1.0f, mx = a > 1.0f ? a : 1.0f;
+    float x = mn * (1.0f / mx);
+    float t = x * x;
+    float r = ((((((((((-0.0121323213173444f * t) + 0.0536813784310406f) * t) - 0.1173503194786851f) * t) + 0.1938924977115610f) * t) - 0.3326756418091246f) * t)
+               + 0.9999793128310355f) * x;
+    r = r + (a > 1.0f ? 1.0f : 0.0f) * (r * -2.0f + 1.57079632679489661923f);
+    return r * sign(a);
 }
+// atan(y, x) of GLSL as _atan2 expands it: rotate the left half plane by pi/2, tan = |s / t| (1 when |x| == |y|)
 static inline float atan2(float y, float x) {
-    if (x != x || y != y) return bits2f(0x7fc00000u);
-    const float PI_F = 3.14159265358979323846f, PIO2_F = 1.57079632679489661923f;
-    if (x == 0.0f) return (y > 0.0f) ? PIO2_F : ((y < 0.0f) ? -PIO2_F : 0.0f);
-    float a = atan_pos(std::fabs(y / x));
-    if (x < 0.0f) a = PI_F - a;
-    return (y < 0.0f) ? -a : a;
+    bool flip = 0.0f >= x;
+    float s = flip ? std::fabs(x) : y;
+    float t = flip ? y : std::fabs(x);
+    float scale = (std::fabs(t) >= 1e18f) ? 0.25f : 1.0f;
+    float rcp = 1.0f / (t * scale);
+    float sot = (s * scale) * rcp;
+    float tn = (std::fabs(x) == std::fabs(y)) ? 1.0f : std::fabs(sot);
+    float arc = atan_pos(tn);
+    arc = arc + (flip ? 1.0f : 0.0f) * 1.57079632679489661923f;
+    float m = y < rcp ? y : rcp;
+    return (m < 0.0f) ? -arc : arc;
 }
 
 }  // namespace lfom

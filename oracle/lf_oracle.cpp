@@ -4,8 +4,11 @@
 // GLSL built-ins are restated the way Mesa's GLSL front end + llvmpipe evaluate them (the only runnable
 // reference implementation): normalize(v) = v * (1/sqrt(dot(v,v))), min/max with
 // x86 MINPS/MAXPS operand semantics, dot() summed left to right, mat*vec summed column by column,
-// inverse() by cofactors times 1/det.  Transcendentals: lf_math_oracle.h (plain-fp32 Cephes kernels; llvmpipe uses
-// its own polynomial approximations and the north_star tolerances absorb the difference).
+// inverse() by cofactors times 1/det, x / y = x * (1 / y) (Mesa lowers every float division to MUL(x, RCP(y)) and
+// gallivm's RCP is the correctly rounded 1 / y), mix(a, b, t) = a * (1 - t) + b * t, refract() with
+// k = 1 - eta * (eta * (1 - d * d)).  Transcendentals: lf_math_oracle.h restates llvmpipe's own polynomial
+// evaluations.  All of these are pinned bit for bit by executing the GLSL on llvmpipe (oracle/_ref/lp_probe,
+// tests/golden/llvmpipe_builtins.npz).
 #include "lf_oracle.h"
 #include "lf_math_oracle.h"
 
@@ -27,10 +30,12 @@ static inline vec3 V3(float a, float b, float c) { return {a, b, c}; }
 static inline vec3 operator+(vec3 a, vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 static inline vec3 operator-(vec3 a, vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 static inline vec3 operator*(vec3 a, vec3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
-static inline vec3 operator/(vec3 a, vec3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }
+// GLSL x / y on Mesa: x * (1 / y), two roundings (FDIV_TO_MUL_RCP; pinned with lp_probe)
+static inline float fdiv(float a, float b) { return a * (1.0f / b); }
+static inline vec3 operator/(vec3 a, vec3 b) { return {fdiv(a.x, b.x), fdiv(a.y, b.y), fdiv(a.z, b.z)}; }
 static inline vec3 operator*(vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 static inline vec3 operator*(float s, vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
-static inline vec3 operator/(vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+static inline vec3 operator/(vec3 a, float s) { float r = 1.0f / s; return {a.x * r, a.y * r, a.z * r}; }
 static inline vec3 operator-(vec3 a) { return {-a.x, -a.y, -a.z}; }
 static inline vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 static inline vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
@@ -50,12 +55,12 @@ static inline float gmin(float a, float b) { return a < b ? a : b; }
 static inline vec3 gmax(vec3 a, vec3 b) { return {gmax(a.x, b.x), gmax(a.y, b.y), gmax(a.z, b.z)}; }
 static inline vec3 gmin(vec3 a, vec3 b) { return {gmin(a.x, b.x), gmin(a.y, b.y), gmin(a.z, b.z)}; }
 static inline float clampf(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
-static inline float mixf(float a, float b, float t) { return a + (b - a) * t; }   // TGSI LRP as llvmpipe emits it
+static inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }   // as Mesa lowers mix() for llvmpipe (pinned with lp_probe)
 static inline vec3 mix3(vec3 a, vec3 b, float t) { return {mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t)}; }
 static inline vec3 reflect(vec3 I, vec3 N) { return I - (2.0f * dot(N, I)) * N; }
 static inline vec3 refract(vec3 I, vec3 N, float eta) {
     float ndi = dot(N, I);
-    float k = 1.0f - eta * eta * (1.0f - ndi * ndi);
+    float k = 1.0f - eta * (eta * (1.0f - ndi * ndi));   // Mesa's builtin: mul(eta, mul(eta, ...))
     if (k < 0.0f) return V3(0.0f);
     return eta * I - (eta * ndi + sqrtf(k)) * N;
 }
@@ -236,24 +241,29 @@ static inline vec2 conditional(const Oracle* o, float u, float v) {
     const float* p = o->scene.hdr_conditional + 2 * ((size_t)nearestIdx(v, H) * W + nearestIdx(u, W));
     return {p[0], p[1]};
 }
-// GL_RGBA8 2D array, GL_LINEAR, GL_REPEAT, fp32 lerp of texel/255 (llvmpipe lerps in 8-bit fixed point; parity
-// scenes use block-constant textures where both agree exactly).
+// GL_RGBA8 2D array, GL_LINEAR, GL_REPEAT the way llvmpipe filters 8-bit formats (its AoS path, pinned bit for bit with
+// oracle/_ref/lp_probe): texel coordinates in 24.8 fixed point, X = round_to_nearest_even(u * W * 256) - 128, texel
+// floor(X / 256) and its +1 neighbour (wrapped), weight X & 255; each lerp is v0 + ((w * (v1 - v0)) >> 8) on the 8-bit
+// channel values (floor, no rounding), x first, then y; the 8-bit result times the float constant 1/255.
+static inline int lerp8(int w, int v0, int v1) { return (v0 + ((w * (v1 - v0)) >> 8)) & 255; }
+static vec4 tex8Linear(const uint8_t* base, int W, int H, float u, float v) {
+    int X = (int)nearbyintf(u * (float)W * 256.0f) - 128, Y = (int)nearbyintf(v * (float)H * 256.0f) - 128;
+    int wx = X & 255, wy = Y & 255;
+    int x0 = wrapi(X >> 8, W), x1 = wrapi((X >> 8) + 1, W), y0 = wrapi(Y >> 8, H), y1 = wrapi((Y >> 8) + 1, H);
+    const uint8_t* a = base + 4 * ((size_t)y0 * W + x0);
+    const uint8_t* b = base + 4 * ((size_t)y0 * W + x1);
+    const uint8_t* c = base + 4 * ((size_t)y1 * W + x0);
+    const uint8_t* d = base + 4 * ((size_t)y1 * W + x1);
+    float r[4];
+    for (int k = 0; k < 4; k++) r[k] = (float)lerp8(wy, lerp8(wx, a[k], b[k]), lerp8(wx, c[k], d[k])) * (float)(1.0 / 255.0);
+    return {r[0], r[1], r[2], r[3]};
+}
 static vec4 texArrayLinear(const Oracle* o, float u, float v, int layer, LfCounters* cnt) {
     int W = o->scene.tex_width, H = o->scene.tex_height;
     if (layer < 0) layer = 0;
     if (layer >= o->scene.num_textures) layer = o->scene.num_textures - 1;
     if (cnt) cnt->tex_samples++;
-    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
-    float fx = floorf(x), fy = floorf(y);
-    float wx = x - fx, wy = y - fy;
-    int x0 = wrapi((int)fx, W), x1 = wrapi((int)fx + 1, W), y0 = wrapi((int)fy, H), y1 = wrapi((int)fy + 1, H);
-    const uint8_t* base = o->scene.texture_maps + (size_t)4 * W * H * layer;
-    auto T = [&](int xx, int yy) { const uint8_t* p = base + 4 * ((size_t)yy * W + xx); return vec4{p[0] / 255.0f, p[1] / 255.0f, p[2] / 255.0f, p[3] / 255.0f}; };
-    vec4 a = T(x0, y0), b = T(x1, y0), c = T(x0, y1), d = T(x1, y1);
-    auto L = [](float p, float q, float w) { return p + (q - p) * w; };
-    vec4 top = {L(a.x, b.x, wx), L(a.y, b.y, wx), L(a.z, b.z, wx), L(a.w, b.w, wx)};
-    vec4 bot = {L(c.x, d.x, wx), L(c.y, d.y, wx), L(c.z, d.z, wx), L(c.w, d.w, wx)};
-    return {L(top.x, bot.x, wy), L(top.y, bot.y, wy), L(top.z, bot.z, wy), L(top.w, bot.w, wy)};
+    return tex8Linear(o->scene.texture_maps + (size_t)4 * W * H * layer, W, H, u, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,7 +285,7 @@ static float SphereIntersect(float rad, vec3 pos, const Ray& r) {   // intersect
 static float RectIntersect(vec3 pos, vec3 u, vec3 v, vec4 plane, const Ray& r) {   // intersection.glsl:30-50
     vec3 n = {plane.x, plane.y, plane.z};
     float dt = dot(r.direction, n);
-    float t = (plane.w - dot(n, r.origin)) / dt;
+    float t = fdiv(plane.w - dot(n, r.origin), dt);
     if (t > EPS) {
         vec3 p = r.origin + r.direction * t;
         vec3 vi = p - pos;
@@ -332,7 +342,7 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
                     if (d < t) {
                         t = d;
                         float cosTheta = dot(-r.direction, normal);
-                        float pdf = (t * t) / (L.area * cosTheta);
+                        float pdf = fdiv(t * t, L.area * cosTheta);
                         lightSampleRec.emission = L.emission;
                         lightSampleRec.pdf = pdf;
                         state.isEmitter = true;
@@ -347,7 +357,7 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
                     if (d < 0.f) d = INFINITY_;
                     if (d < t) {
                         t = d;
-                        float pdf = (t * t) / L.area;
+                        float pdf = fdiv(t * t, L.area);
                         lightSampleRec.emission = L.emission;
                         lightSampleRec.pdf = pdf;
                         state.isEmitter = true;
@@ -399,7 +409,8 @@ static float Traverse(Inv& g, const Ray& r, State& state, LightSampleRec& lightS
                 uvt.x = dot(tv, pv);
                 uvt.y = dot(r_trans.direction, qv);
                 uvt.z = dot(e1, qv);
-                uvt.x = uvt.x / det; uvt.y = uvt.y / det; uvt.z = uvt.z / det;
+                float rdet = 1.0f / det;   // uvt.xyz / det = uvt.xyz * rcp(det)
+                uvt.x = uvt.x * rdet; uvt.y = uvt.y * rdet; uvt.z = uvt.z * rdet;
                 uvt.w = 1.0f - uvt.x - uvt.y;
                 bool inside = uvt.x >= 0.f && uvt.y >= 0.f && uvt.z >= 0.f && uvt.w >= 0.f;
                 if (ANY) {
@@ -475,7 +486,7 @@ static vec3 ImportanceSampleGTR1(float rgh, float r1, float r2) {   // sampling.
     float a = gmax(0.001f, rgh);
     float a2 = a * a;
     float phi = r1 * TWO_PI;
-    float cosTheta = sqrtf((1.0f - lfom::pow(a2, 1.0f - r1)) / (1.0f - a2));
+    float cosTheta = sqrtf(fdiv(1.0f - lfom::pow(a2, 1.0f - r1), 1.0f - a2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi;
     lfom::sincos(phi, sinPhi, cosPhi);
@@ -485,7 +496,7 @@ static vec3 ImportanceSampleGTR1(float rgh, float r1, float r2) {   // sampling.
 static vec3 ImportanceSampleGTR2(float rgh, float r1, float r2) {   // sampling.glsl:37-49
     float a = gmax(0.001f, rgh);
     float phi = r1 * TWO_PI;
-    float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
+    float cosTheta = sqrtf(fdiv(1.0f - r2, 1.0f + (a * a - 1.0f) * r2));
     float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
     float sinPhi, cosPhi;
     lfom::sincos(phi, sinPhi, cosPhi);
@@ -500,20 +511,20 @@ static float DielectricFresnel(float cos_theta_i, float eta) {   // sampling.gls
     float sinThetaTSq = eta * eta * (1.0f - cos_theta_i * cos_theta_i);
     if (sinThetaTSq > 1.0f) return 1.0f;
     float cos_theta_t = sqrtf(gmax(1.0f - sinThetaTSq, 0.0f));
-    float rs = (eta * cos_theta_t - cos_theta_i) / (eta * cos_theta_t + cos_theta_i);
-    float rp = (eta * cos_theta_i - cos_theta_t) / (eta * cos_theta_i + cos_theta_t);
+    float rs = fdiv(eta * cos_theta_t - cos_theta_i, eta * cos_theta_t + cos_theta_i);
+    float rp = fdiv(eta * cos_theta_i - cos_theta_t, eta * cos_theta_i + cos_theta_t);
     return 0.5f * (rs * rs + rp * rp);
 }
 static float GTR1(float NDotH, float a) {   // sampling.glsl:79-87
     if (a >= 1.0f) return (1.0f / PI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (PI * lfom::log(a2) * t);
+    return fdiv(a2 - 1.0f, PI * lfom::log(a2) * t);
 }
 static float GTR2(float NDotH, float a) {   // sampling.glsl:90-96
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return a2 / (PI * t * t);
+    return fdiv(a2, PI * t * t);
 }
 static float SmithG_GGX(float NDotV, float alphaG) {   // sampling.glsl:110-116
     float a = alphaG * alphaG;
@@ -541,7 +552,7 @@ static vec3 UniformSampleSphere(float r1, float r2) {   // sampling.glsl:153-160
 }
 static float powerHeuristic(float a, float b) {   // sampling.glsl:163-169
     float t = a * a;
-    return t / (b * b + t);
+    return fdiv(t, b * b + t);
 }
 static void sampleSphereLight(Inv& g, const Light& light, vec3 surfacePos, LightSampleRec& rec) {   // sampling.glsl:172-189
     float r1 = rnd(g), r2 = rnd(g);
@@ -552,7 +563,7 @@ static void sampleSphereLight(Inv& g, const Light& light, vec3 surfacePos, Light
     rec.direction /= rec.dist;
     rec.normal = normalize(lightSurfacePos - light.position);
     rec.emission = light.emission * (float)g.o->scene.num_lights;
-    rec.pdf = distSq / (light.area * fabsf(dot(rec.normal, rec.direction)));
+    rec.pdf = fdiv(distSq, light.area * fabsf(dot(rec.normal, rec.direction)));
 }
 static void sampleRectLight(Inv& g, const Light& light, vec3 surfacePos, LightSampleRec& rec) {   // sampling.glsl:192-206
     float r1 = rnd(g), r2 = rnd(g);
@@ -563,7 +574,7 @@ static void sampleRectLight(Inv& g, const Light& light, vec3 surfacePos, LightSa
     rec.direction /= rec.dist;
     rec.normal = normalize(cross(light.u, light.v));
     rec.emission = light.emission * (float)g.o->scene.num_lights;
-    rec.pdf = distSq / (light.area * fabsf(dot(rec.normal, rec.direction)));
+    rec.pdf = fdiv(distSq, light.area * fabsf(dot(rec.normal, rec.direction)));
 }
 static void sampleDistantLight(Inv& g, const Light& light, vec3 surfacePos, LightSampleRec& rec) {   // sampling.glsl:209-216
     rec.direction = normalize(light.position - V3(0.0f));
@@ -584,7 +595,7 @@ static float EnvPdf(Inv& g, const Ray& r) {   // sampling.glsl:236-243
     float pdf = conditional(g.o, uv.x, uv.y).y * marginal(g.o, uv.y).y;
     float st, ct;
     lfom::sincos(theta, st, ct);
-    return (pdf * (float)(g.o->scene.hdr_width * g.o->scene.hdr_height)) / (2.0f * PI * PI * st);
+    return fdiv(pdf * (float)(g.o->scene.hdr_width * g.o->scene.hdr_height), 2.0f * PI * PI * st);
 }
 static vec4 EnvSample(Inv& g, vec3& color) {   // sampling.glsl:246-265
     float r1 = rnd(g), r2 = rnd(g);
@@ -600,7 +611,7 @@ static vec4 EnvSample(Inv& g, vec3& color) {   // sampling.glsl:246-265
     lfom::sincos(phi, sph, cph);
     if (st == 0.0f) pdf = 0.0f;
     float hdrResolution = (float)(g.o->scene.hdr_width * g.o->scene.hdr_height);
-    return {-st * cph, ct, -st * sph, (pdf * hdrResolution) / (2.0f * PI * PI * st)};
+    return {-st * cph, ct, -st * sph, fdiv(pdf * hdrResolution, 2.0f * PI * PI * st)};
 }
 static vec3 EmitterSample(const State& state, const LightSampleRec& lrec, const BsdfSampleRec& brec) {   // sampling.glsl:271-282
     if (state.depth == 0) return lrec.emission;
@@ -615,7 +626,7 @@ static vec3 EvalDielectricReflection(const State& s, vec3 V, vec3 N, vec3 L, vec
     if (dot(N, L) <= 0.0f) return V3(0.0f);
     float F = DielectricFresnel(dot(V, H), s.eta);
     float D = GTR2(dot(N, H), s.mat.roughness);
-    pdf = D * dot(N, H) * F / (4.0f * fabsf(dot(V, H)));
+    pdf = fdiv(D * dot(N, H) * F, 4.0f * fabsf(dot(V, H)));
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return s.mat.albedo * F * D * G;
 }
@@ -625,7 +636,7 @@ static vec3 EvalDielectricRefraction(const State& s, vec3 V, vec3 N, vec3 L, vec
     float F = DielectricFresnel(fabsf(dot(V, H)), s.eta);
     float D = GTR2(dot(N, H), s.mat.roughness);
     float denomSqrt = dot(L, H) + dot(V, H) * s.eta;
-    pdf = D * dot(N, H) * (1.0f - F) * fabsf(dot(L, H)) / (denomSqrt * denomSqrt);
+    pdf = fdiv(D * dot(N, H) * (1.0f - F) * fabsf(dot(L, H)), denomSqrt * denomSqrt);
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
     return s.mat.albedo * (1.0f - F) * D * G * fabsf(dot(V, H)) * fabsf(dot(L, H)) * 4.0f * s.eta * s.eta / (denomSqrt * denomSqrt);
 }
@@ -633,7 +644,7 @@ static vec3 EvalSpecular(const State& s, vec3 Cspec0, vec3 V, vec3 N, vec3 L, ve
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return V3(0.0f);
     float D = GTR2(dot(N, H), s.mat.roughness);
-    pdf = D * dot(N, H) / (4.0f * dot(V, H));
+    pdf = fdiv(D * dot(N, H), 4.0f * dot(V, H));
     float FH = SchlickFresnel(dot(L, H));
     vec3 F = mix3(Cspec0, V3(1.0f), FH);
     float G = SmithG_GGX(fabsf(dot(N, L)), s.mat.roughness) * SmithG_GGX(fabsf(dot(N, V)), s.mat.roughness);
@@ -643,7 +654,7 @@ static vec3 EvalClearcoat(const State& s, vec3 V, vec3 N, vec3 L, vec3 H, float&
     pdf = 0.0f;
     if (dot(N, L) <= 0.0f) return V3(0.0f);
     float D = GTR1(dot(N, H), mixf(0.1f, 0.001f, s.mat.clearcoatRoughness));
-    pdf = D * dot(N, H) / (4.0f * dot(V, H));
+    pdf = fdiv(D * dot(N, H), 4.0f * dot(V, H));
     float FH = SchlickFresnel(dot(L, H));
     float F = mixf(0.04f, 1.0f, FH);
     float G = SmithG_GGX(dot(N, L), 0.25f) * SmithG_GGX(dot(N, V), 0.25f);
@@ -943,7 +954,7 @@ static vec3 PathTrace(Inv& g, Ray r) {   // pathtrace.glsl:208-295
 // renderer.glsl
 // ------------------------------------------------------------------------------------------------
 static inline float mapf(float value, float low1, float high1, float low2, float high2) {   // renderer.glsl:20-23
-    return low2 + ((value - low1) * (high2 - low2)) / (high1 - low1);
+    return low2 + fdiv((value - low1) * (high2 - low2), high1 - low1);
 }
 
 // renderer.glsl:27-62: pixel mapping, RNG init, jitter, thin-lens camera ray.  Returns the full-frame pixel.
@@ -975,12 +986,12 @@ static Ray CameraRay(Inv& g, int lx, int ly, int tileX, int tileY, int frame, in
     vec2 jitter;
     jitter.x = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
     jitter.y = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
-    jitter.x /= (screenResolution.x * 0.5f);
-    jitter.y /= (screenResolution.y * 0.5f);
+    jitter.x = fdiv(jitter.x, screenResolution.x * 0.5f);
+    jitter.y = fdiv(jitter.y, screenResolution.y * 0.5f);
     vec2 d = coordsTile + jitter;
 
-    float scale = tanf(C.fov * 0.5f);
-    d.y *= screenResolution.y / screenResolution.x * scale;
+    float scale = lfom::tan(C.fov * 0.5f);
+    d.y *= fdiv(screenResolution.y, screenResolution.x) * scale;
     d.x *= scale;
     vec3 right = {C.right[0], C.right[1], C.right[2]}, up = {C.up[0], C.up[1], C.up[2]}, fwd = {C.forward[0], C.forward[1], C.forward[2]};
     vec3 pos = {C.position[0], C.position[1], C.position[2]};
@@ -1011,11 +1022,11 @@ static Ray PreviewRay(Inv& g, int x, int y, int pvW, int pvH, bool useDof) {
     vec2 jitter;
     jitter.x = r1 < 1.0f ? sqrtf(r1) - 1.0f : 1.0f - sqrtf(2.0f - r1);
     jitter.y = r2 < 1.0f ? sqrtf(r2) - 1.0f : 1.0f - sqrtf(2.0f - r2);
-    jitter.x /= screenResolution.x;
-    jitter.y /= screenResolution.y;
+    jitter.x = fdiv(jitter.x, screenResolution.x);
+    jitter.y = fdiv(jitter.y, screenResolution.y);
     vec2 d = {(2.0f * TexCoords.x - 1.0f) + jitter.x, (2.0f * TexCoords.y - 1.0f) + jitter.y};
-    float scale = tanf(C.fov * 0.5f);
-    d.y *= screenResolution.y / screenResolution.x * scale;
+    float scale = lfom::tan(C.fov * 0.5f);
+    d.y *= fdiv(screenResolution.y, screenResolution.x) * scale;
     d.x *= scale;
     vec3 right = {C.right[0], C.right[1], C.right[2]}, up = {C.up[0], C.up[1], C.up[2]}, fwd = {C.forward[0], C.forward[1], C.forward[2]};
     vec3 pos = {C.position[0], C.position[1], C.position[2]};
@@ -1123,6 +1134,43 @@ void Oracle::RandKat(int px, int py, int frame, int n, uint32_t* seedx, float* v
     std::memset(&g, 0, sizeof g);
     InitRNG(g, vec2{(float)px + 0.5f, (float)py + 0.5f}, frame);
     for (int i = 0; i < n; i++) { values[i] = rnd(g); seedx[i] = g.seed[0]; }
+}
+
+// The expression groups of tests/golden/make_builtin_golden.py, evaluated with this file's restatement of the GLSL built-ins.
+void Oracle::BuiltinKat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int texW, int texH, int texL) {
+    for (int i = 0; i < n; i++) {
+        const float* a = in4 + 4 * (size_t)i;
+        float* r = out4 + 4 * (size_t)i;
+        r[0] = r[1] = r[2] = r[3] = 0.0f;
+        switch (op) {
+        case 0: { float s, c; lfom::sincos(a[0], s, c); r[0] = s; r[1] = c; r[2] = lfom::tan(a[1]); r[3] = sqrtf(fabsf(a[2])); break; }   // vec4(sin(a.x), cos(a.x), tan(a.y), sqrt(abs(a.z)))
+        case 1: r[0] = lfom::exp(a[0]); r[1] = lfom::log(a[1]); r[2] = lfom::pow(a[1], a[2]); r[3] = lfom::acos(a[3]); break;          // vec4(exp(a.x), log(a.y), pow(a.y, a.z), acos(a.w))
+        case 2: r[0] = lfom::atan2(a[0], a[1]); r[1] = fdiv(a[0], a[1]); r[2] = mixf(a[0], a[1], a[2]); r[3] = inversesqrt(fabsf(a[3])); break;   // vec4(atan(a.x, a.y), a.x / a.y, mix(a.x, a.y, a.z), inversesqrt(abs(a.w)))
+        case 3: {   // vec4(refract(normalize(a.xyz), normalize(a.zxy * vec3(1, -1, 1) + 0.1), a.w), 0)
+            vec3 I = normalize(vec3{a[0], a[1], a[2]});
+            vec3 N = normalize(vec3{a[2], a[0], a[1]} * vec3{1.0f, -1.0f, 1.0f} + V3(0.1f));
+            vec3 q = refract(I, N, a[3]);
+            r[0] = q.x; r[1] = q.y; r[2] = q.z;
+            break;
+        }
+        case 4: {   // vec4(reflect(normalize(a.xyz), normalize(a.zxy * vec3(1, -1, 1) + 0.1)), length(a.xyz))
+            vec3 I = normalize(vec3{a[0], a[1], a[2]});
+            vec3 N = normalize(vec3{a[2], a[0], a[1]} * vec3{1.0f, -1.0f, 1.0f} + V3(0.1f));
+            vec3 q = reflect(I, N);
+            r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = length(vec3{a[0], a[1], a[2]});
+            break;
+        }
+        case 5: {   // texture(tex8, a.xyz): RGBA8 array, LINEAR, REPEAT
+            int layer = (int)floorf(a[2] + 0.5f);
+            if (layer < 0) layer = 0;
+            if (layer >= texL) layer = texL - 1;
+            vec4 t = tex8Linear(tex + (size_t)4 * texW * texH * layer, texW, texH, a[0], a[1]);
+            r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+            break;
+        }
+        default: break;
+        }
+    }
 }
 
 }  // namespace lforacle

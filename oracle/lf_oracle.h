@@ -46,6 +46,11 @@ struct Oracle {
 
     // rand() known-answer probe: the first n draws after InitRNG((px+.5, py+.5), frame) (globals.glsl:116-133).
     static void RandKat(int px, int py, int frame, int n, uint32_t* seedx, float* values);
+
+    // GLSL built-in known-answer probe (tests/golden/llvmpipe_builtins.npz, made by executing the same expressions on
+    // llvmpipe): n vec4 arguments -> n vec4 results of expression group `op` (see the switch in lf_oracle.cpp).
+    // `tex` (W x H x L RGBA8, for the texture-filter group) may be null otherwise.
+    static void BuiltinKat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int texW, int texH, int texL);
 };
 
 }  // namespace lforacle

@@ -57,6 +57,9 @@ void lforacle_sample(void* hv, int lx, int ly, int tile_x, int tile_y, int frame
 void lforacle_rand_kat(int px, int py, int frame, int n, uint32_t* seedx, float* values) {
     lforacle::Oracle::RandKat(px, py, frame, n, seedx, values);
 }
+void lforacle_builtin_kat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int tex_w, int tex_h, int tex_l) {
+    lforacle::Oracle::BuiltinKat(op, in4, n, out4, tex, tex_w, tex_h, tex_l);
+}
 void lforacle_get_counters(void* hv, LfCounters* out) { *out = static_cast<Handle*>(hv)->oracle->counters; }
 void lforacle_reset_counters(void* hv) { std::memset(&static_cast<Handle*>(hv)->oracle->counters, 0, sizeof(LfCounters)); }
 

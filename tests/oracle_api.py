@@ -37,6 +37,7 @@ def load_oracle():
     lib.lforacle_primary_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lforacle_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lforacle_rand_kat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.lforacle_builtin_kat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.lforacle_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     lib.lforacle_reset_counters.argtypes = [C.c_void_p]
     _lib = lib
@@ -108,3 +109,17 @@ def rand_kat(px, py, frame, n=4):
     vals = np.zeros(n, np.float32)
     lib.lforacle_rand_kat(px, py, frame, n, seed.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p))
     return seed, vals
+
+
+def builtin_kat(op, args, tex=None):
+    """The oracle's restatement of GLSL built-ins on (n, 4) float32 arguments (expression group `op`, lf_oracle.cpp BuiltinKat)."""
+    lib = load_oracle()
+    a = np.ascontiguousarray(args, np.float32)
+    out = np.empty_like(a)
+    if tex is not None:
+        tex = np.ascontiguousarray(tex, np.uint8)
+        lib.lforacle_builtin_kat(op, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p), tex.ctypes.data_as(C.c_void_p),
+                                 tex.shape[2], tex.shape[1], tex.shape[0])
+    else:
+        lib.lforacle_builtin_kat(op, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p), None, 0, 0, 0)
+    return out

@@ -1,0 +1,92 @@
+"""CPU tests: the SOURCE TEXT of the CUDA device functions, compiled for the host, against the oracle - bit for bit.
+
+tests/hostcheck/lf_hostcheck.cpp compiles lavaframe_b200/csrc/{lf_math,lf_device,lf_shade}.cuh with g++ (-ffp-contract=off
+mirrors nvcc -fmad=false), supplies the handful of device intrinsics, and runs k_megakernel's per-sample loop on the CPU over
+the arrays lf_repack.cpp makes for the GPU.  Any statement of the kernels that departs from the oracle (and, through the
+oracle's own golden tests, from the reference on llvmpipe) shows up here without a GPU.  It is a checker: nothing in the
+product links or calls it, and the `-m gpu` tests remain the parity tests proper (they exercise the real kernels, the
+warp-cooperative traversal, the texture objects and the device's arithmetic).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_api import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HC_DIR = os.path.join(ROOT, "tests", "hostcheck")
+CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+
+SCENES = ["cornell", "c2mini", "c3mini"]
+
+
+@pytest.fixture(scope="session")
+def hostcheck():
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    subprocess.run(["make", "-s", "-C", HC_DIR], check=True)
+    lib = C.CDLL(os.path.join(HC_DIR, "liblfhostcheck.so"))
+    lib.lfhc_open_pack.restype = C.c_void_p
+    lib.lfhc_open_pack.argtypes = [C.c_char_p]
+    lib.lfhc_close.argtypes = [C.c_void_p]
+    lib.lfhc_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.lfhc_render_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lfhc_render_preview.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+def _open(lib, golden_dir, name):
+    pack = os.path.join(golden_dir, f"{name}.lfpack")
+    h = lib.lfhc_open_pack(pack.encode())
+    assert h, f"hostcheck cannot open {pack}"
+    w, hh = C.c_int(), C.c_int()
+    lib.lfhc_size(h, C.byref(w), C.byref(hh))
+    return pack, h, w.value, hh.value
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_source_matches_oracle(golden_dir, oracle_lib, hostcheck, name):
+    pack, h, W, H = _open(hostcheck, golden_dir, name)
+    n = 4
+    img = np.zeros((H, W, 3), np.float32)
+    culled = np.zeros((H, W, 3), np.float32)
+    assert hostcheck.lfhc_render_frames(h, 2, n, 1, 0, img.ctypes.data) == 0
+    assert hostcheck.lfhc_render_frames(h, 2, n, 1, 1, culled.ctypes.data) == 0
+    strided = np.zeros((H, W, 3), np.float32)
+    assert hostcheck.lfhc_render_frames(h, 3, 2, 2, 1, strided.ctypes.data) == 0      # frames 3, 5: a rank's share of an spp split
+    hostcheck.lfhc_close(h)
+    o = Oracle(pack)
+    ref = o.render_frames(2, n)
+    ref_strided = o.render_frames(3, 2, frame_stride=2)
+    o.close()
+    assert np.array_equal(img, ref), f"{name}: device source differs from the oracle on {np.mean((img != ref).any(axis=2)):.6f} of pixels"
+    assert np.array_equal(culled, img), f"{name}: the distance cull changes the image"
+    assert np.array_equal(strided, ref_strided)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_source_matches_llvmpipe(golden_dir, hostcheck, name):
+    """... and therefore the reference itself: the 1-spp golden image of the unmodified GLSL on llvmpipe, bit for bit."""
+    g = np.load(os.path.join(golden_dir, f"{name}_llvmpipe.npz"))
+    pack, h, W, H = _open(hostcheck, golden_dir, name)
+    img = np.zeros((H, W, 3), np.float32)
+    assert hostcheck.lfhc_render_frames(h, 2, 1, 1, 1, img.ctypes.data) == 0
+    hostcheck.lfhc_close(h)
+    bits = float(np.mean((img == g["spp1"]).all(axis=2)))
+    assert bits >= 0.9999, f"{name}: bit-identical to llvmpipe on {bits:.6f} of pixels"
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_source_preview_matches_oracle(golden_dir, oracle_lib, hostcheck, name):
+    pack, h, W, H = _open(hostcheck, golden_dir, name)
+    o = Oracle(pack)
+    for pw, ph, dof in ((W // 2, H // 2, 0), (W, H, 1)):
+        img = np.zeros((ph, pw, 3), np.float32)
+        assert hostcheck.lfhc_render_preview(h, pw, ph, 2, dof, img.ctypes.data) == 0
+        ref = o.render_preview(pw, ph, 2, bool(dof))
+        assert np.array_equal(img, ref), f"{name} preview {pw}x{ph} dof={dof}: differs on {np.mean((img != ref).any(axis=2)):.6f} of pixels"
+    o.close()
+    hostcheck.lfhc_close(h)

@@ -43,15 +43,18 @@ CORNELL_KAT = [
 
 SCENES = ["cornell", "c2mini", "c3mini"]
 
-# Fraction of pixels whose 1-spp radiance must be within 1e-3 of the reference-on-llvmpipe, and of the N-spp mean.
-# Cornell (all diffuse) meets the north_star bar of 99.9 %.  The glass / rough-metal / textured scenes cannot, for
-# ANY implementation that is not bit-identical to llvmpipe in every operation: (i) specular chains amplify last-ulp
-# differences of sin/cos/pow (llvmpipe uses its own polynomials) into different branch decisions - merely enabling
-# FMA contraction in this oracle moves 0.9 % of c2mini's pixels by more than 1e-3; (ii) llvmpipe filters RGBA8
-# textures in 8-bit fixed point, which differs at the block edges of the textures.  Primary
-# hit IDs agree on 100 % of pixels in all three scenes, which pins traversal and geometry exactly.
-MIN_SPP1 = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.98}
-MIN_SPPN = {"cornell": 0.99, "c2mini": 0.90, "c3mini": 0.85}
+# Fraction of pixels whose 1-spp radiance must be within 1e-3 of the reference-on-llvmpipe (north_star: 99.9 %), and of the
+# N-spp mean.  Since the oracle restates llvmpipe's own evaluation of every GLSL built-in (test_builtins_bit_exact below),
+# its x * (1 / y) division and its 8-bit texture filter, the 1-spp images are BIT-IDENTICAL on every pixel of all three
+# scenes, glass, rough metal, clearcoat and textures included.  The one thing no implementation can reproduce is the
+# reference's read of an unwritten material when the nearest hit is an analytic light (pathtrace.glsl:246-253 runs
+# GetMaterialsAndTextures on a State whose matID was never set; llvmpipe leaves the temporaries uninitialised, and the same
+# binary returns different values from run to run): those pixels are counted in the bars below, and excluded only from the
+# bit-identity check of the N-spp mean.
+MIN_SPP1 = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999}
+MIN_SPP1_BITS = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999}
+MIN_SPPN = {"cornell": 0.999, "c2mini": 0.999, "c3mini": 0.97}     # c3mini: 7 % of its pixels look straight at a light
+MIN_SPPN_BITS_NO_EMITTER = 0.999
 
 
 def _pack(golden_dir, name):
@@ -67,6 +70,21 @@ def test_rand_kat(oracle_lib):
         if seeds is not None:
             assert [int(x) for x in s] == seeds
         np.testing.assert_allclose(v, np.array(vals, np.float32), rtol=0, atol=1e-9)
+
+
+def _same_bits(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+
+
+@pytest.mark.parametrize("group", range(6))
+def test_builtins_bit_exact(golden_dir, oracle_lib, group):
+    """The oracle's GLSL built-ins against llvmpipe EXECUTING them (tests/golden/make_builtin_golden.py): sin cos tan sqrt |
+    exp log pow acos | atan(y,x) `/` mix inversesqrt | refract | reflect length | RGBA8 LINEAR/REPEAT texture filter."""
+    from oracle_api import builtin_kat
+    g = np.load(os.path.join(golden_dir, "llvmpipe_builtins.npz"))
+    out = builtin_kat(group, g[f"in{group}"], tex=g["tex"] if group == 5 else None)
+    same = _same_bits(out, g[f"out{group}"])
+    assert same.all(), f"{g['expr'][group]}: {int((~same).sum())} of {same.size} values differ from llvmpipe"
 
 
 def test_cornell_pack_matches_reference_dump(golden_dir):
@@ -116,9 +134,14 @@ def test_oracle_vs_llvmpipe(golden_dir, oracle_lib, name):
     s1 = o.render_frames(2, 1)
     frac = radiance_agreement(s1, g["spp1"])
     assert frac >= MIN_SPP1[name], f"{name}: 1-spp radiance within 1e-3 on {frac:.6f} of pixels"
+    bits = float(np.mean((s1 == g["spp1"]).all(axis=2)))
+    assert bits >= MIN_SPP1_BITS[name], f"{name}: 1-spp radiance bit-identical to llvmpipe on {bits:.6f} of pixels"
     n = int(g["nspp"])
     sN = o.render_frames(2, n) / np.float32(n)
     assert radiance_agreement(sN, g["sppN"], rel=1e-3) >= MIN_SPPN[name]
+    surface = em == 0                                   # first hit is not an analytic light (see the note above)
+    bitsN = float(np.mean((sN == g["sppN"]).all(axis=2)[surface]))
+    assert bitsN >= MIN_SPPN_BITS_NO_EMITTER, f"{name}: {n}-spp mean bit-identical on {bitsN:.6f} of the non-emitter pixels"
     assert rmse_over_mean_luminance(sN, g["sppN"]) < 0.05
     o.close()
 
@@ -149,7 +172,7 @@ def test_cull_preserves_results(golden_dir, oracle_lib, name):
 
 
 # Same reasoning as MIN_SPP1: the Cornell box is pinned at the north_star bar, glass / metal / textures cannot be.
-MIN_PREVIEW = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.97}
+MIN_PREVIEW = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.99}   # c3mini: emitter pixels, see above
 
 
 @pytest.mark.parametrize("name", SCENES)
