@@ -362,6 +362,34 @@ def _c4(outdir, name, res, depth=8, grid=36):
     return path
 
 
+def c4_gold(outdir, grid=14):
+    """The C4 recipe inside llvmpipe's limits and a fixture's size: grid x grid instances (196) of one 1 984-triangle sphere,
+    the same four materials (2 diffuse, metal, glass) in the same pattern, one sphere light, depth 8, 512x256 (power of two,
+    see c2_mini).  tests/golden/c4gold_llvmpipe.npz pins the instanced deep-bounce path against the reference."""
+    assets = reference_assets(outdir)
+    v, n, t = displaced_sphere(32, 32, 1.0)
+    write_obj(os.path.join(assets, "c4gold_sphere.obj"), v, n, t)
+    s = _renderer(512, 256, 8)
+    s += _camera((0, 4.5, -12.5), (0, 0, -1), 42)
+    s += _material("diffuse_a", albedo=(0.75, 0.7, 0.65))
+    s += _material("diffuse_b", albedo=(0.3, 0.5, 0.75), roughness=0.8)
+    s += _material("metal", albedo=(0.95, 0.85, 0.6), metallic=1.0, roughness=0.15)
+    s += _material("glass", albedo=(1, 1, 1), transmission=1.0, ior=1.45, roughness=0.03)
+    mats = ["diffuse_a", "diffuse_b", "metal", "glass"]
+    k = 0
+    for gz in range(grid):
+        for gx in range(grid):
+            x = (gx - (grid - 1) / 2) * 1.0
+            z = (gz - (grid - 1) / 2) * 1.0
+            y = 0.25 * math.sin(0.7 * gx) * math.cos(0.5 * gz)
+            s += _mesh("c4gold_sphere.obj", mats[(gx * 7 + gz * 3 + k) % 4], (x, y, z), (0.4, 0.4, 0.4))
+            k += 1
+    s += _sphere_light((0, 7, -3), 0.8, (40, 38, 35))
+    path = os.path.join(assets, "c4gold.scene")
+    open(path, "w").write(s)
+    return path
+
+
 def c4_stress(outdir):
     """C4/C5: 1296 x glass_sphere.obj = 20.57 M instanced triangles, 1 sphere light, depth 8, 3840x2160."""
     return _c4(outdir, "c4stress", (3840, 2160))
@@ -373,7 +401,7 @@ def c4_mini(outdir):
 
 
 SCENES = {"cornell_256": cornell_256, "c2_mini": c2_mini, "c2_full": c2_full, "c3_mini": c3_mini, "c3_full": c3_full,
-          "c4_stress": c4_stress, "c4_mini": c4_mini}
+          "c4_stress": c4_stress, "c4_mini": c4_mini, "c4_gold": c4_gold}
 
 
 def build_pack(name, outdir):

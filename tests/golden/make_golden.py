@@ -40,6 +40,7 @@ SCENES = {
     "cornell": (gen_scenes.cornell_256, 64),
     "c2mini": (gen_scenes.c2_mini, 16),
     "c3mini": (gen_scenes.c3_mini, 16),
+    "c4gold": (gen_scenes.c4_gold, 8),
 }
 
 
@@ -75,8 +76,10 @@ def tiled_cornell(spp=4, tile=64):
         print("cornell tiled", spp, "spp mean", img.mean(axis=(0, 1)), info)
 
 
-def preview_goldens():
+def preview_goldens(only=None):
     for name, (builder, _) in SCENES.items():
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             scene = builder(os.path.join(tmp, "assets"))
             arrays = {}
@@ -92,9 +95,11 @@ def preview_goldens():
 
 
 def main(names):
-    if "preview" in names:
-        preview_goldens()
-        names = [n for n in names if n != "preview"]
+    if "preview" in names:                      # `preview` alone = every scene; `preview c4gold` = that scene's preview only
+        rest = [n for n in names if n != "preview"]
+        preview_goldens(rest or None)
+        if rest:
+            return
     if "tiled" in names:
         tiled_cornell()
         names = [n for n in names if n != "tiled"]

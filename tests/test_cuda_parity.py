@@ -11,7 +11,7 @@ import lavaframe_b200 as lf
 
 pytestmark = pytest.mark.gpu
 
-SCENES = ["cornell", "c2mini", "c3mini"]
+SCENES = ["cornell", "c2mini", "c3mini", "c4gold"]
 
 
 def pack_path(golden_dir, name):
@@ -64,8 +64,8 @@ def test_primary_hits_vs_llvmpipe(tracer, golden_dir, name):
 def test_radiance_vs_oracle(tracer, golden_dir, oracle_lib, name, mode):
     """Check 2, CUDA vs oracle, wavefront (mode 0) and megakernel (mode 1): 1-spp radiance of frame 2 and an 8-frame sum
     must be IDENTICAL BIT FOR BIT on every pixel - diffuse, glass, rough metal, clearcoat, textures, env map alike.
-    Both sides evaluate the same fp32 expression trees without FMA contraction and the same plain-fp32 transcendental
-    kernels (lf_math.cuh / lf_math_oracle.h), so there is no tolerance to hide a bug in."""
+    Both sides evaluate the same fp32 expression trees without FMA contraction and the same plain-fp32 restatement of
+    llvmpipe's transcendental kernels (lf_math.cuh / lf_math_oracle.h), so there is no tolerance to hide a bug in."""
     pack = lf.ScenePack(pack_path(golden_dir, name))
     tracer.upload_pack(pack, kernel_mode=mode)
     o = Oracle(pack.path)
@@ -79,8 +79,11 @@ def test_radiance_vs_oracle(tracer, golden_dir, oracle_lib, name, mode):
     o.close()
 
 
-# CUDA vs the reference on llvmpipe: bounded by how well ANY implementation can match llvmpipe (tests/test_oracle_golden.py)
-MIN_VS_LLVMPIPE = {"cornell": 0.999, "c2mini": 0.97, "c3mini": 0.98}
+# CUDA vs the reference on llvmpipe.  The kernels restate llvmpipe's own evaluation of every GLSL built-in, its x * (1 / y)
+# division and its 8-bit texture filter, so the 1-spp image is bit-identical to the reference's on every pixel
+# (tests/test_oracle_golden.py explains the one exception in multi-sample images: the reference's own undefined read of
+# an unwritten material on pixels that look straight at an analytic light).
+MIN_VS_LLVMPIPE = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999, "c4gold": 0.9999}
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -90,8 +93,11 @@ def test_radiance_vs_llvmpipe(tracer, golden_dir, name):
     tracer.upload_pack(lf.ScenePack(pack_path(golden_dir, name)))
     tracer.clear()
     tracer.render_frames(2, 1)
-    frac = radiance_agreement(tracer.read_accum(), g["spp1"])
+    img = tracer.read_accum()
+    frac = radiance_agreement(img, g["spp1"])
     assert frac >= MIN_VS_LLVMPIPE[name], f"{name}: 1-spp within 1e-3 on {frac:.6f}"
+    bits = float(np.mean((img == g["spp1"]).all(axis=2)))
+    assert bits >= MIN_VS_LLVMPIPE[name], f"{name}: 1-spp bit-identical to the reference on llvmpipe on {bits:.6f} of pixels"
     n = int(g["nspp"])
     tracer.clear()
     tracer.render_frames(2, n)
@@ -131,7 +137,7 @@ def test_preview_engine(tracer, golden_dir, oracle_lib, name):
         ref = o.render_preview(w, h, 2, dof)
         assert np.array_equal(img, ref), f"{name}/{key}: {int((img != ref).any(axis=2).sum())} pixels differ from the oracle"
         frac = radiance_agreement(img, g[key])
-        assert frac >= MIN_VS_LLVMPIPE[name] - 0.01, f"{name}/{key}: within 1e-3 of llvmpipe on {frac:.6f}"
+        assert frac >= (0.99 if name == "c3mini" else 0.9999), f"{name}/{key}: within 1e-3 of llvmpipe on {frac:.6f}"   # c3mini: emitter pixels
     img = tracer.render_preview(77, 45, pack.max_depth, False)
     assert np.array_equal(img, o.render_preview(77, 45, pack.max_depth, False))
     o.close()

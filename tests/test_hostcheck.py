@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HC_DIR = os.path.join(ROOT, "tests", "hostcheck")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
 
-SCENES = ["cornell", "c2mini", "c3mini"]
+SCENES = ["cornell", "c2mini", "c3mini", "c4gold"]
 
 
 @pytest.fixture(scope="session")

@@ -41,7 +41,7 @@ CORNELL_KAT = [
     ((170, 60), 0.850257, 36, 4, (0, 0, 0)),
 ]
 
-SCENES = ["cornell", "c2mini", "c3mini"]
+SCENES = ["cornell", "c2mini", "c3mini", "c4gold"]
 
 # Fraction of pixels whose 1-spp radiance must be within 1e-3 of the reference-on-llvmpipe (north_star: 99.9 %), and of the
 # N-spp mean.  Since the oracle restates llvmpipe's own evaluation of every GLSL built-in (test_builtins_bit_exact below),
@@ -51,9 +51,9 @@ SCENES = ["cornell", "c2mini", "c3mini"]
 # GetMaterialsAndTextures on a State whose matID was never set; llvmpipe leaves the temporaries uninitialised, and the same
 # binary returns different values from run to run): those pixels are counted in the bars below, and excluded only from the
 # bit-identity check of the N-spp mean.
-MIN_SPP1 = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999}
-MIN_SPP1_BITS = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999}
-MIN_SPPN = {"cornell": 0.999, "c2mini": 0.999, "c3mini": 0.97}     # c3mini: 7 % of its pixels look straight at a light
+MIN_SPP1 = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999, "c4gold": 0.9999}
+MIN_SPP1_BITS = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.9999, "c4gold": 0.9999}
+MIN_SPPN = {"cornell": 0.999, "c2mini": 0.999, "c3mini": 0.97, "c4gold": 0.999}     # c3mini: 7 % of its pixels look straight at a light
 MIN_SPPN_BITS_NO_EMITTER = 0.999
 
 
@@ -172,7 +172,7 @@ def test_cull_preserves_results(golden_dir, oracle_lib, name):
 
 
 # Same reasoning as MIN_SPP1: the Cornell box is pinned at the north_star bar, glass / metal / textures cannot be.
-MIN_PREVIEW = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.99}   # c3mini: emitter pixels, see above
+MIN_PREVIEW = {"cornell": 0.9999, "c2mini": 0.9999, "c3mini": 0.99, "c4gold": 0.9999}   # c3mini: emitter pixels, see above
 
 
 @pytest.mark.parametrize("name", SCENES)
