@@ -10,6 +10,7 @@
 // Xlib (fakex11.c) — see SURVEY.md Appendix H.
 //
 //   lf_ref_llvmpipe --scene S --spp N --out img.f32 [--probe hits] [--timing-json]
+//                   [--tonemap I] [--vignette INTENSITY POWER] [--ca DISTORTION(0|1) DISTANCE P1 P2 P3]   (RenderOptions the UI sets, Main.cpp:470-500)
 //   lf_ref_llvmpipe --extract-assets DIR        (writes the reference's build_include/assets tree)
 //
 // Output image: W*H*3 float32, rows bottom-up, = GetOutputBufferHDR with tonemapIndex 0
@@ -106,6 +107,9 @@ int main(int argc, char** argv) {
     int spp = 1;
     bool timingJson = false, previewDof = false;
     float previewScale = 0.f;                        // > 0: render the preview engine's image instead (--preview SCALE)
+    int tonemap = 0;
+    bool useVignette = false, useCA = false, caDistortion = false;
+    float vigI = 0.f, vigP = 1.f, caDist = 0.05f, caP1 = 5.f, caP2 = -0.5f, caP3 = 0.5f;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> std::string { return i + 1 < argc ? argv[++i] : ""; };
@@ -118,6 +122,12 @@ int main(int argc, char** argv) {
         else if (a == "--timing-json") timingJson = true;
         else if (a == "--preview") previewScale = (float)atof(next().c_str());
         else if (a == "--preview-dof") previewDof = true;
+        else if (a == "--tonemap") tonemap = atoi(next().c_str());
+        else if (a == "--vignette") { useVignette = true; vigI = (float)atof(next().c_str()); vigP = (float)atof(next().c_str()); }
+        else if (a == "--ca") {
+            useCA = true; caDistortion = atoi(next().c_str()) != 0; caDist = (float)atof(next().c_str());
+            caP1 = (float)atof(next().c_str()); caP2 = (float)atof(next().c_str()); caP3 = (float)atof(next().c_str());
+        }
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
     if (!extractDir.empty()) {
@@ -186,7 +196,9 @@ int main(int argc, char** argv) {
     double tLoad0 = now();
     if (!LoadSceneFromFile(sceneFile, GlobalState.scene, ro)) return 4;
     double tLoad1 = now();
-    ro.tonemapIndex = 0;
+    ro.tonemapIndex = tonemap;
+    ro.useVignette = useVignette; ro.vignetteIntensity = vigI; ro.vignettePower = vigP;
+    ro.useCA = useCA; ro.useCADistortion = caDistortion; ro.caDistance = caDist; ro.caP1 = caP1; ro.caP2 = caP2; ro.caP3 = caP3;
     GlobalState.scene->renderOptions = ro;          // Main.cpp:969
     GlobalState.scene->camera->isMoving = false;    // never initialised by Camera's ctor (Camera.cpp:101-117)
 
