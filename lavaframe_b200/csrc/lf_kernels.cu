@@ -11,6 +11,7 @@
 // and the post-process kernel (postprocess.glsl tonemappers) used by the read-back calls.
 #include "lf_device.cuh"
 #include "lf_shade.cuh"
+#include "lf_post.cuh"
 #include "lf_kernels.h"
 
 namespace lf {
@@ -429,65 +430,12 @@ __global__ void k_export_hits(DevScene S, DevParams P, PathSoA A, float* t, int*
     }
 }
 
-// postprocess.glsl:26-172: color = accum * invSampleCounter (or the chromatic-aberration fetches), tonemap, vignette.
-LFD float tm_aces(float c) { return clampf((c * (2.51f * c + 0.03f)) / (c * (2.43f * c + 0.59f) + 0.14f), 0.0f, 1.0f); }
-LFD float tm_kanjero(float c, bool rgb) {
-    float v = powf((c * (c * (1.2295f * c + 0.3135f) + 1.1935f * 0.4655f) / (c * (1.1935f * c + 0.4655f) + 0.073f)), 1.7f);
-    if (rgb) v = powf(v, 1.0f / 0.8f);
-    v *= 0.8f;
-    return clampf(v, 0.0f, 1.0f);
-}
-LFD float tm_hejl(float c) { c = gmax(0.0f, c - 0.004f); return (c * (6.2f * c + .5f)) / (c * (6.2f * c + 1.7f) + 0.06f); }
-LFD float tm_uncharted(float c) {
-    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
-    return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
-}
-// accumTexture is LINEAR / MIRRORED_REPEAT (TiledRenderer.cpp:165-173): bilinear fetch at a normalised coordinate
-LFD int mirrori(int i, int n) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
-LFD float accum_linear(const float* __restrict__ accum, int W, int H, float u, float v, int ch) {
-    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
-    float fx = floorf(x), fy = floorf(y);
-    float wx = x - fx, wy = y - fy;
-    int x0 = mirrori((int)fx, W), x1 = mirrori((int)fx + 1, W), y0 = mirrori((int)fy, H), y1 = mirrori((int)fy + 1, H);
-    float a = accum[3 * ((size_t)y0 * W + x0) + ch], b = accum[3 * ((size_t)y0 * W + x1) + ch];
-    float c = accum[3 * ((size_t)y1 * W + x0) + ch], e = accum[3 * ((size_t)y1 * W + x1) + ch];
-    float top = a + (b - a) * wx, bot = c + (e - c) * wx;
-    return top + (bot - top) * wy;
-}
+// postprocess.glsl:26-172 (lf_post.cuh): color = accum * invSampleCounter (or the chromatic-aberration fetches), tonemap, vignette.
 __global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned char* out_u8, int W, int H, float inv, int tonemap, LfPostParams pp) {
     const int n = W * H;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int px = i % W, py = i / W;
-        const float tu = ((float)px + 0.5f) / (float)W, tv = ((float)py + 0.5f) / (float)H;   // TexCoords of the fullscreen quad
-        float c[3] = {accum[3 * i] * inv, accum[3 * i + 1] * inv, accum[3 * i + 2] * inv};
-        if (pp.use_ca) {   // chromaticAberration(), postprocess.glsl:96-118: red and blue fetched at +/- an offset
-            float offset = pp.ca_distance;
-            float dx = tu - pp.ca_p3, dy = tv - pp.ca_p3;
-            float dist = 0.f + (powf(sqrtf(dx * dx + dy * dy), pp.ca_p1) * pp.ca_p2);
-            float o = pp.use_ca_distortion ? offset * dist : (offset * 0.025f) * pp.ca_p2;
-            c[0] = accum_linear(accum, W, H, tu + o, tv + o, 0) * inv;
-            c[2] = accum_linear(accum, W, H, tu - o, tv - o, 2) * inv;
-        }
-        const float g = 1.0f / 2.2f;
-        if (tonemap == 1) {
-            float lum = 0.3f * c[0] + 0.6f * c[1] + 0.1f * c[2];
-            for (int k = 0; k < 3; k++) c[k] = powf(c[k] * 1.0f / (1.0f + lum / 2.f), g);
-        } else if (tonemap == 2) {
-            for (int k = 0; k < 3; k++) c[k] = powf(tm_aces(c[k]), g);
-        } else if (tonemap == 3) {
-            for (int k = 0; k < 3; k++) c[k] = powf(clampf(c[k] / (c[k] + 1.f), 0.0f, 1.0f), g);
-        } else if (tonemap == 4) {
-            for (int k = 0; k < 3; k++) c[k] = powf(tm_kanjero(c[k], true), g);
-        } else if (tonemap == 5) {
-            for (int k = 0; k < 3; k++) c[k] = tm_hejl(c[k]);
-        } else if (tonemap == 6) {
-            for (int k = 0; k < 3; k++) c[k] = powf(tm_uncharted(c[k]), g) * 1.75f;
-        }
-        if (pp.use_vignette) {   // vignette(), postprocess.glsl:121-124
-            float dx = tu - 0.5f, dy = tv - 0.5f;
-            float d = 1.0f - powf(sqrtf(dx * dx + dy * dy), pp.vignette_power) * pp.vignette_intensity;
-            for (int k = 0; k < 3; k++) c[k] *= d;
-        }
+        float c[3];
+        post_pixel(accum, W, H, i, inv, tonemap, pp, c);
         if (out_f) { out_f[3 * i] = c[0]; out_f[3 * i + 1] = c[1]; out_f[3 * i + 2] = c[2]; }
         if (out_u8)
             for (int k = 0; k < 3; k++) out_u8[3 * i + k] = (unsigned char)__float2int_rn(clampf(c[k], 0.0f, 1.0f) * 255.0f);   // GL float -> unorm8

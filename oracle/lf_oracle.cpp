@@ -1136,6 +1136,71 @@ void Oracle::RandKat(int px, int py, int frame, int n, uint32_t* seedx, float* v
     for (int i = 0; i < n; i++) { values[i] = rnd(g); seedx[i] = g.seed[0]; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// postprocess.glsl
+// ------------------------------------------------------------------------------------------------
+static inline float tmACES(float c) { return clampf(fdiv(c * (2.51f * c + 0.03f), c * (2.43f * c + 0.59f) + 0.14f), 0.0f, 1.0f); }   // postprocess.glsl:34-43
+static inline float tmKanjero(float c) {   // :69-84 (the alpha channel skips the second pow; it is not part of the RGB output)
+    float v = lfom::pow(fdiv(c * (c * (1.2295f * c + 0.3135f) + 1.1935f * 0.4655f), c * (1.1935f * c + 0.4655f) + 0.073f), 1.7f);
+    v = lfom::pow(v, 1.0f / 0.8f);
+    v *= 0.8f;
+    return clampf(v, 0.0f, 1.0f);
+}
+static inline float tmHejl(float c) { c = gmax(0.0f, c - 0.004f); return fdiv(c * (6.2f * c + .5f), c * (6.2f * c + 1.7f) + 0.06f); }   // :52-56
+static inline float tmUncharted(float c) {   // :87-96
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return fdiv(c * (A * c + C * B) + D * E, c * (A * c + B) + D * F) - fdiv(E, F);
+}
+static inline int mirrori(int i, int n) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+// texture(pathTraceTexture, uv).ch: RGB32F, LINEAR, MIRRORED_REPEAT (TiledRenderer.cpp:165-173)
+static float accumLinear(const float* accum, int W, int H, float u, float v, int ch) {
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float wx = x - fx, wy = y - fy;
+    int x0 = mirrori((int)fx, W), x1 = mirrori((int)fx + 1, W), y0 = mirrori((int)fy, H), y1 = mirrori((int)fy + 1, H);
+    float a = accum[3 * ((size_t)y0 * W + x0) + ch], b = accum[3 * ((size_t)y0 * W + x1) + ch];
+    float c = accum[3 * ((size_t)y1 * W + x0) + ch], e = accum[3 * ((size_t)y1 * W + x1) + ch];
+    float top = a + (b - a) * wx, bot = c + (e - c) * wx;
+    return top + (bot - top) * wy;
+}
+void Oracle::PostProcess(const float* accum, int W, int H, float inv, int tonemapIndex, const LfPostParams& pp, float* out) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < W * H; i++) {
+        const int px = i % W, py = i / W;
+        const float tu = ((float)px + 0.5f) / (float)W, tv = ((float)py + 0.5f) / (float)H;   // TexCoords at the fragment centre
+        float c[3] = {accum[3 * (size_t)i] * inv, accum[3 * (size_t)i + 1] * inv, accum[3 * (size_t)i + 2] * inv};   // :129-133
+        if (pp.use_ca) {   // chromaticAberration(), :98-118
+            float offset = pp.ca_distance;
+            float dx = tu - pp.ca_p3, dy = tv - pp.ca_p3;
+            float dist = 0.f + (lfom::pow(sqrtf(dx * dx + dy * dy), pp.ca_p1) * pp.ca_p2);
+            float o = pp.use_ca_distortion ? offset * dist : (offset * 0.025f) * pp.ca_p2;
+            c[0] = accumLinear(accum, W, H, tu + o, tv + o, 0) * inv;
+            c[2] = accumLinear(accum, W, H, tu - o, tv - o, 2) * inv;
+        }
+        const float g = 1.0f / 2.2f;
+        switch (tonemapIndex) {   // :135-165
+        case 1: {   // pow(tonemap(color, 2), 1 / 2.2), tonemap = c * 1.0 / (1.0 + luminance / limit) (:26-31)
+            float lum = (0.3f * c[0] + 0.6f * c[1]) + 0.1f * c[2];
+            float r = 1.0f / (1.0f + fdiv(lum, 2.f));
+            for (int k = 0; k < 3; k++) c[k] = lfom::pow((c[k] * 1.0f) * r, g);
+            break;
+        }
+        case 2: for (int k = 0; k < 3; k++) c[k] = lfom::pow(tmACES(c[k]), g); break;
+        case 3: for (int k = 0; k < 3; k++) c[k] = lfom::pow(clampf(fdiv(c[k], c[k] + 1.f), 0.0f, 1.0f), g); break;   // Reinhard, :46-49
+        case 4: for (int k = 0; k < 3; k++) c[k] = lfom::pow(tmKanjero(c[k]), g); break;
+        case 5: for (int k = 0; k < 3; k++) c[k] = tmHejl(c[k]); break;
+        case 6: for (int k = 0; k < 3; k++) c[k] = lfom::pow(tmUncharted(c[k]), g) * 1.75f; break;
+        default: break;
+        }
+        if (pp.use_vignette) {   // vignette(), :121-124
+            float dx = tu - 0.5f, dy = tv - 0.5f;
+            float d = 1.0f - lfom::pow(sqrtf(dx * dx + dy * dy), pp.vignette_power) * pp.vignette_intensity;
+            for (int k = 0; k < 3; k++) c[k] *= d;
+        }
+        out[3 * (size_t)i] = c[0]; out[3 * (size_t)i + 1] = c[1]; out[3 * (size_t)i + 2] = c[2];
+    }
+}
+
 // The expression groups of tests/golden/make_builtin_golden.py, evaluated with this file's restatement of the GLSL built-ins.
 void Oracle::BuiltinKat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int texW, int texH, int texL) {
     for (int i = 0; i < n; i++) {

@@ -47,6 +47,11 @@ struct Oracle {
     // rand() known-answer probe: the first n draws after InitRNG((px+.5, py+.5), frame) (globals.glsl:116-133).
     static void RandKat(int px, int py, int frame, int n, uint32_t* seedx, float* values);
 
+    // The post-process pass (shaders/postprocess.glsl:126-172, drawn by TiledRenderer::Render into tileOutputTexture,
+    // TiledRenderer.cpp:346-350): out = tonemap(accum * inv) with optional chromatic aberration and vignette.
+    // accum / out: W*H*3 floats, rows bottom-up.
+    static void PostProcess(const float* accum, int W, int H, float inv, int tonemapIndex, const LfPostParams& pp, float* out);
+
     // GLSL built-in known-answer probe (tests/golden/llvmpipe_builtins.npz, made by executing the same expressions on
     // llvmpipe): n vec4 arguments -> n vec4 results of expression group `op` (see the switch in lf_oracle.cpp).
     // `tex` (W x H x L RGBA8, for the texture-filter group) may be null otherwise.

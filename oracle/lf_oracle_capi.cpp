@@ -57,6 +57,11 @@ void lforacle_sample(void* hv, int lx, int ly, int tile_x, int tile_y, int frame
 void lforacle_rand_kat(int px, int py, int frame, int n, uint32_t* seedx, float* values) {
     lforacle::Oracle::RandKat(px, py, frame, n, seedx, values);
 }
+void lforacle_post_process(const float* accum, int w, int h, float inv, int tonemap_index, const LfPostParams* pp, float* out) {
+    LfPostParams none;
+    std::memset(&none, 0, sizeof none);
+    lforacle::Oracle::PostProcess(accum, w, h, inv, tonemap_index, pp ? *pp : none, out);
+}
 void lforacle_builtin_kat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int tex_w, int tex_h, int tex_l) {
     lforacle::Oracle::BuiltinKat(op, in4, n, out4, tex, tex_w, tex_h, tex_l);
 }

@@ -17,7 +17,9 @@ and lavaframe_b200/bin/lf_scenepack by CMake):
         while camera->isMoving, read back from previewFBO): half = previewScale 0.5, maxDepth 2;
         full_dof = previewScale 1.0 with "#define USE_DOF"
 
-Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [cornell4096] [preview] [tiled] ...
+  * cornell64_llvmpipe_post.npz    the post-process pass: every tonemapper, vignette, chromatic aberration (see post_goldens)
+
+Usage:  python tests/golden/make_golden.py [cornell] [c2mini] [c3mini] [c4gold] [cornell4096] [preview] [tiled] [post] ...
 """
 import json
 import os
@@ -76,6 +78,40 @@ def tiled_cornell(spp=4, tile=64):
         print("cornell tiled", spp, "spp mean", img.mean(axis=(0, 1)), info)
 
 
+POST_CASES = {   # name -> (tonemapIndex, vignette (intensity, power) or None, chromatic aberration (distortion, distance, p1, p2, p3) or None)
+    "tm1": (1, None, None), "tm2": (2, None, None), "tm3": (3, None, None), "tm4": (4, None, None), "tm5": (5, None, None),
+    "tm6": (6, None, None), "tm2_vig": (2, (0.6, 1.5), None), "ca0": (0, None, (0, 0.05, 5.0, -0.5, 0.5)),
+    "ca1": (0, None, (1, 0.05, 5.0, -0.5, 0.5)), "tm3_ca1_vig": (3, (0.4, 2.0), (1, 0.08, 3.0, -0.7, 0.45)),
+}
+
+
+def post_goldens(spp=4):
+    """cornell64_llvmpipe_post.npz: GetOutputBufferHDR of the reference for every tonemapper, the vignette and both chromatic
+    aberration modes (RenderOptions the UI sets, Main.cpp:470-500; postprocess.glsl) on the Cornell box at 64x64, `spp` samples.
+    tm0 (identity) * spp is the accumulation buffer the other images were made from (the scale is a power of two: exact)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        scene = gen_scenes.cornell_256(os.path.join(tmp, "assets"), res=(64, 64))
+        arrays = {"nspp": np.int32(spp)}
+
+        def run(extra):
+            out = os.path.join(tmp, "o.f32")
+            res = subprocess.run([REFBIN, "--scene", scene, "--spp", str(spp), "--out", out, "--timing-json"] + extra,
+                                 env=gen_scenes.llvmpipe_env(), check=True, capture_output=True, text=True)
+            info = json.loads(res.stdout.strip().splitlines()[-1])
+            return np.fromfile(out, np.float32).reshape(info["height"], info["width"], 3)
+
+        arrays["tm0"] = run([])
+        for name, (tm, vig, ca) in POST_CASES.items():
+            extra = ["--tonemap", str(tm)]
+            if vig:
+                extra += ["--vignette", str(vig[0]), str(vig[1])]
+            if ca:
+                extra += ["--ca"] + [str(v) for v in ca]
+            arrays[name] = run(extra)
+            print("post", name, arrays[name].mean(axis=(0, 1)))
+        np.savez_compressed(os.path.join(GOLD, "cornell64_llvmpipe_post.npz"), **arrays)
+
+
 def preview_goldens(only=None):
     for name, (builder, _) in SCENES.items():
         if only and name not in only:
@@ -100,6 +136,9 @@ def main(names):
         preview_goldens(rest or None)
         if rest:
             return
+    if "post" in names:
+        post_goldens()
+        names = [n for n in names if n != "post"]
     if "tiled" in names:
         tiled_cornell()
         names = [n for n in names if n != "tiled"]

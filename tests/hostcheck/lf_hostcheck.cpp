@@ -45,6 +45,7 @@ template <class T> static inline T tex2DLayered(cudaTextureObject_t obj, float x
 }
 
 #include "lf_shade.cuh"
+#include "lf_post.cuh"
 #include "lf_repack.h"
 #include "scenepack.h"
 
@@ -199,6 +200,14 @@ int lfhc_render_preview(void* h, int pv_w, int pv_h, int max_depth, int use_dof,
         }
     }
     return 0;
+}
+
+// k_post for a W x H accumulation buffer
+void lfhc_post_process(const float* accum, int W, int H, float inv, int tonemap, const LfPostParams* pp, float* out) {
+    LfPostParams p;
+    std::memset(&p, 0, sizeof p);
+    if (pp) p = *pp;
+    for (int i = 0; i < W * H; i++) post_pixel(accum, W, H, i, inv, tonemap, p, out + 3 * (size_t)i);
 }
 
 }  // extern "C"

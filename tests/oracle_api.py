@@ -37,6 +37,7 @@ def load_oracle():
     lib.lforacle_primary_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lforacle_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lforacle_rand_kat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.lforacle_post_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     lib.lforacle_builtin_kat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.lforacle_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     lib.lforacle_reset_counters.argtypes = [C.c_void_p]
@@ -122,4 +123,14 @@ def builtin_kat(op, args, tex=None):
                                  tex.shape[2], tex.shape[1], tex.shape[0])
     else:
         lib.lforacle_builtin_kat(op, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p), None, 0, 0, 0)
+    return out
+
+
+def post_process(accum, inv, tonemap_index, post=None):
+    """postprocess.glsl as the oracle restates it: accum (H, W, 3) float32 rows bottom-up -> output image.  `post` = lavaframe_b200.LfPostParams or None."""
+    lib = load_oracle()
+    a = np.ascontiguousarray(accum, np.float32)
+    out = np.empty_like(a)
+    lib.lforacle_post_process(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], float(inv), int(tonemap_index),
+                              C.cast(C.byref(post), C.c_void_p) if post is not None else None, out.ctypes.data_as(C.c_void_p))
     return out

@@ -306,6 +306,28 @@ def test_postprocess_ca_and_vignette(tracer, golden_dir):
     np.testing.assert_array_equal(tracer.read_output(0.25, 0), acc * np.float32(0.25))
 
 
+def test_postprocess_vs_oracle_and_llvmpipe(tracer, golden_dir, oracle_lib):
+    """SURVEY 8(f) row 1 at the parity bar of the hot path: k_post (6 tonemappers, vignette, both chromatic-aberration modes)
+    bit-identical to the oracle's PostProcess, and to the reference's own GetOutputBufferHDR on llvmpipe
+    (tests/golden/cornell64_llvmpipe_post.npz: Cornell at 64x64, 4 spp); the 4-spp image itself must match the reference's."""
+    from oracle_api import post_process
+    from test_oracle_golden import _post_cases
+    accum, inv, cases = _post_cases(golden_dir)
+    H, W, _ = accum.shape
+    pack = lf.ScenePack(pack_path(golden_dir, "cornell"))
+    tracer.upload_pack(pack, width=W, height=H, tile_width=W, tile_height=H)
+    tracer.clear(); tracer.render_frames(2, int(round(1 / inv)))
+    acc = tracer.read_accum()
+    assert np.array_equal(acc, accum), f"the {int(round(1 / inv))}-spp accumulation differs from the reference's on {(acc != accum).any(axis=2).mean():.6f} of pixels"
+    for name, tm, pp, ref in cases:
+        tracer.set_post(pp)
+        out = tracer.read_output(inv, tm)
+        assert np.array_equal(out, post_process(acc, inv, tm, pp)), f"{name}: k_post differs from the oracle"
+        same = float(np.mean(out == ref))
+        assert same >= (0.999 if name == "tm3_ca1_vig" else 1.0), f"{name}: {same:.6f} of the values bit-identical to llvmpipe"
+    tracer.set_post(None)
+
+
 def test_errors_are_reported(gpu):
     pt = lf.PathTracer(gpu)
     with pytest.raises(lf.LfCudaError, match="no scene"):

@@ -35,6 +35,7 @@ def hostcheck():
     lib.lfhc_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lfhc_render_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lfhc_render_preview.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lfhc_post_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -90,3 +91,15 @@ def test_device_source_preview_matches_oracle(golden_dir, oracle_lib, hostcheck,
         assert np.array_equal(img, ref), f"{name} preview {pw}x{ph} dof={dof}: differs on {np.mean((img != ref).any(axis=2)):.6f} of pixels"
     o.close()
     hostcheck.lfhc_close(h)
+
+
+def test_device_source_postprocess_matches_oracle(golden_dir, oracle_lib, hostcheck):
+    """lf_post.cuh (k_post's per-pixel function) against the oracle's PostProcess, and through it the reference's output."""
+    from oracle_api import post_process
+    from test_oracle_golden import _post_cases
+    accum, inv, cases = _post_cases(golden_dir)
+    H, W, _ = accum.shape
+    for name, tm, pp, ref in cases:
+        out = np.empty_like(accum)
+        hostcheck.lfhc_post_process(accum.ctypes.data, W, H, inv, tm, C.cast(C.byref(pp), C.c_void_p), out.ctypes.data)
+        assert np.array_equal(out, post_process(accum, inv, tm, pp)), name

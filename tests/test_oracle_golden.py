@@ -219,3 +219,38 @@ def test_tiled_render_vs_llvmpipe(golden_dir, oracle_lib):
     img = acc / np.float32(n)
     assert radiance_agreement(img, g["sppN"]) >= 0.999
     assert rmse_over_mean_luminance(img, g["sppN"]) < 0.005
+
+
+def _post_cases(golden_dir):
+    """(name, tonemapIndex, LfPostParams or None, reference image) of tests/golden/cornell64_llvmpipe_post.npz + the accumulation buffer."""
+    import importlib.util
+    import lavaframe_b200 as lf
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(golden_dir, "cornell64_llvmpipe_post.npz"))
+    n = int(g["nspp"])
+    accum = g["tm0"] * np.float32(n)            # exact: n is a power of two
+    cases = []
+    for name, (tm, vig, ca) in mg.POST_CASES.items():
+        pp = lf.LfPostParams()
+        if vig:
+            pp.use_vignette, pp.vignette_intensity, pp.vignette_power = 1, vig[0], vig[1]
+        if ca:
+            pp.use_ca, pp.use_ca_distortion, pp.ca_distance, pp.ca_p1, pp.ca_p2, pp.ca_p3 = 1, ca[0], ca[1], ca[2], ca[3], ca[4]
+        cases.append((name, tm, pp, g[name]))
+    return accum, 1.0 / n, cases
+
+
+def test_postprocess_vs_llvmpipe(golden_dir, oracle_lib):
+    """the oracle's postprocess.glsl (6 tonemappers, vignette, both chromatic-aberration modes) against the
+    reference's own GetOutputBufferHDR on llvmpipe, bit for bit.  One case samples the accumulation texture outside [0, 1]
+    (MIRRORED_REPEAT): llvmpipe mirrors the coordinate in floating point before scaling, which moves 2 of 12 288 values by
+    a few ulp; everything else is identical."""
+    from oracle_api import post_process
+    accum, inv, cases = _post_cases(golden_dir)
+    for name, tm, pp, ref in cases:
+        out = post_process(accum, inv, tm, pp)
+        same = float(np.mean(out == ref))
+        assert same >= (0.999 if name == "tm3_ca1_vig" else 1.0), f"{name}: {same:.6f} of the values bit-identical to llvmpipe"
+        np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-7)
