@@ -17,10 +17,13 @@
 
 namespace lf {
 
-#ifdef LF_INLINE_MATH
-#define LFM __device__ __forceinline__
-#else
+// Inlined by default: with llvmpipe's short polynomials the shade kernel is no longer instruction-cache bound (no_instruction
+// stall 8.8 -> 1.4 per issue) and inlining measures 3 % faster in k_shade (profiles/r1_experiments/ab_l2_persist_inline_math.txt);
+// the Cephes-sized functions of the earlier round were faster out of line.
+#ifdef LF_OUTLINE_MATH
 #define LFM __device__ __noinline__
+#else
+#define LFM __device__ __forceinline__
 #endif
 
 // sin and cos of the same angle (Cephes sinf/cosf: octant reduction with a 3-part pi/4, degree-7/8 polynomials)

@@ -498,32 +498,11 @@ int lfcuda_clear(lfcuda_ctx* ctx) {
     return 0;
 }
 
-// Experiment knob (off unless LF_L2_PERSIST_MB is set): pin the shading normals (the one large array k_shade gathers from at
-// random, 48 bytes per triangle) in a persisting L2 window, so that the path state streaming through L2 does not evict them.
-static void apply_l2_window(lfcuda_ctx* ctx) {
-    static const int mb = [] { const char* e = getenv("LF_L2_PERSIST_MB"); return e ? atoi(e) : 0; }();
-    if (mb <= 0 || !ctx->dev.trinrm || ctx->packed.trinrm.empty()) return;
-    static bool limit_set = false;
-    if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20); limit_set = true; }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, ctx->device);
-    size_t bytes = ctx->packed.trinrm.size() * sizeof(float4);
-    size_t win = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-    cudaStreamAttrValue attr = {};
-    attr.accessPolicyWindow.base_ptr = const_cast<float4*>(ctx->dev.trinrm);
-    attr.accessPolicyWindow.num_bytes = win;
-    attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)(((size_t)mb << 20) / (double)win));
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-}
-
 int lfcuda_render_frames(lfcuda_ctx* ctx, int32_t first_frame, int32_t nframes, int32_t frame_stride, int32_t tile_x, int32_t tile_y) {
     int r = check_ready(ctx);
     if (r) return r;
     if (nframes < 0) return fail(ctx, LFCUDA_EINVAL, "nframes < 0");
     CK(cudaSetDevice(ctx->device));
-    apply_l2_window(ctx);
     for (int done = 0; done < nframes;) {
         int n = std::min(ctx->frames_cap, nframes - done);
         r = run_batch(ctx, first_frame + done * frame_stride, n, frame_stride, tile_x, tile_y, true);
