@@ -66,7 +66,8 @@ def reference_assets(outdir):
 
 
 def write_pack(scene_path, pack_path):
-    subprocess.run([PACKBIN, scene_path, pack_path], check=True)
+    # the tool's summary line goes to OUR stderr: callers such as bench.py own stdout (one JSON line)
+    subprocess.run([PACKBIN, scene_path, pack_path], check=True, stdout=sys.stderr)
     return pack_path
 
 
