@@ -248,7 +248,14 @@ LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, int* s
     if (w.ref >= 0) {                             // inner node (closest_hit.glsl:167-199)
         bump<COUNT>(cnt, C_INNER); if (ANY) bump<COUNT>(cnt, C_INNER_SH);
         const float4* n = S.nodes + (size_t)4 * w.ref;
-#ifndef LF_NODE_LDG128   // 256-bit node loads: extend -4.6 %, shadow -3 % on C2 against 4 x LDG.E.128 (A/B on one box)
+#if defined(LF_NODE_TEX) && LF_NODE_TEX == 1   // experiment: the whole node through the texture unit (4 x TLD4-style float4 fetches)
+        float4 n0 = tex1Dfetch<float4>(S.nodes_tex, 4 * w.ref), n1 = tex1Dfetch<float4>(S.nodes_tex, 4 * w.ref + 1);
+        float4 n2 = tex1Dfetch<float4>(S.nodes_tex, 4 * w.ref + 2), n3 = tex1Dfetch<float4>(S.nodes_tex, 4 * w.ref + 3);
+#elif defined(LF_NODE_TEX) && LF_NODE_TEX == 2   // experiment: half through the LSU (one 256-bit load), half through the texture unit
+        f8 na = ldg8(n);
+        float4 n0 = na.lo, n1 = na.hi;
+        float4 n2 = tex1Dfetch<float4>(S.nodes_tex, 4 * w.ref + 2), n3 = tex1Dfetch<float4>(S.nodes_tex, 4 * w.ref + 3);
+#elif !defined(LF_NODE_LDG128)   // 256-bit node loads: extend -4.6 %, shadow -3 % on C2 against 4 x LDG.E.128 (A/B on one box)
         f8 na = ldg8(n), nb = ldg8(n + 2);
         float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
 #else
@@ -300,8 +307,13 @@ LFD bool walk_leaf(const DevScene& S, const Walk& w, float maxDist, Hit& hit, De
     bump<COUNT>(cnt, C_LEAF); if (ANY) bump<COUNT>(cnt, C_LEAF_SH);
     const int first = ref_leaf_first(w.ref), count = ref_leaf_count(w.ref);
     for (int i = 0; i < count; i++) {
+#ifdef LF_TRI_TEX   // experiment: triangle records through the texture unit
+        const int ti = kTriStride * (first + i);
+        float4 q0 = tex1Dfetch<float4>(S.tris_tex, ti), q1 = tex1Dfetch<float4>(S.tris_tex, ti + 1), q2 = tex1Dfetch<float4>(S.tris_tex, ti + 2);
+#else
         const float4* tp = S.tris + (size_t)kTriStride * (first + i);
         float4 q0 = ldg4(tp), q1 = ldg4(tp + 1), q2 = ldg4(tp + 2);
+#endif
         bump<COUNT>(cnt, C_TRI); if (ANY) bump<COUNT>(cnt, C_TRI_SH);
         f3 e0 = mk3(q1.x, q1.y, q1.z), e1 = mk3(q2.x, q2.y, q2.z);
         f3 pv = cross(w.d, e1);

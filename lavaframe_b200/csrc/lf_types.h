@@ -54,6 +54,8 @@ struct DevScene {
     const float2* conditional;  // hdr_w * hdr_h
     cudaTextureObject_t tex_maps;   // RGBA8 layered 2D, point sampled, raw uchar4 (filtered in fp32 by the kernel)
     cudaTextureObject_t hdr_tex;    // RGBA32F 2D, point sampled (filtered in fp32 by the kernel)
+    cudaTextureObject_t tris_tex;   // the triangle records as a linear float4 texture (LF_TRI_TEX experiment)
+    cudaTextureObject_t nodes_tex;  // the inner-node array as a linear float4 texture (LF_NODE_TEX experiment: node fetches through the TEX pipe)
     int top_ref;
     int num_lights, num_materials, num_instances;
     int tex_w, tex_h, num_tex;

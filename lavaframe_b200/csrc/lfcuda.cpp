@@ -122,6 +122,8 @@ void free_scene(lfcuda_ctx* c) {
     c->scene_allocs.clear();
     if (c->dev.tex_maps) cudaDestroyTextureObject(c->dev.tex_maps);
     if (c->dev.hdr_tex) cudaDestroyTextureObject(c->dev.hdr_tex);
+    if (c->dev.nodes_tex) cudaDestroyTextureObject(c->dev.nodes_tex);
+    if (c->dev.tris_tex) cudaDestroyTextureObject(c->dev.tris_tex);
     if (c->tex_array) cudaFreeArray(c->tex_array);
     if (c->hdr_array) cudaFreeArray(c->hdr_array);
     c->tex_array = c->hdr_array = nullptr;
@@ -384,6 +386,19 @@ int lfcuda_upload_scene(lfcuda_ctx* ctx, const LfSceneView* v) {
     if ((r = upload(ctx, P.lights.data(), P.lights.size(), &lights, ctx->scene_allocs))) return r;
     ctx->d_nodes = nodes; ctx->d_inst = inst; ctx->d_materials = mats; ctx->materials_cap = v->num_materials;
     D.nodes = nodes; D.tris = tris; D.trinrm = trinrm; D.tri_vx = trivx; D.inst = inst; D.materials = mats; D.lights = lights;
+    {   // the same node buffer seen through the texture unit (linear float4 texture; only the LF_NODE_TEX kernel variants read it)
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = nodes;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = ctx->nodes_cap * sizeof(float4);
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        CK(cudaCreateTextureObject(&D.nodes_tex, &rd, &td, nullptr));
+        rd.res.linear.devPtr = tris;
+        rd.res.linear.sizeInBytes = P.tris.size() * sizeof(float4);
+        if (!P.tris.empty()) CK(cudaCreateTextureObject(&D.tris_tex, &rd, &td, nullptr));
+    }
     D.top_ref = P.top_ref;
     D.num_lights = v->num_lights; D.num_materials = v->num_materials; D.num_instances = v->num_instances;
 
