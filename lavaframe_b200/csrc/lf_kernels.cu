@@ -307,7 +307,10 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
 }
 
 // shade, part B: BSDF sample, throughput, Russian roulette, next ray; survivors are appended to the next bounce's queue.
-__global__ void __launch_bounds__(128, 8) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
+#ifndef LF_SAMPLE_MINBLOCKS
+#define LF_SAMPLE_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
     const int count = Q.counts[4 * Q.stride + depth];
     int* next = Q.active[(depth + 1) & 1];
     int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
@@ -509,7 +512,7 @@ void launch_shade(const LaunchCtx& L, int depth) {
     }
 }
 void launch_sample(const LaunchCtx& L, int depth) {
-    k_sample<<<L.sm_count * 8, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
+    k_sample<<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
 }
 void launch_shadow(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;
