@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
 
 // ---------------------------------------------------------------------------------------------- shade
 #ifndef LF_SHADE_MINBLOCKS
-#define LF_SHADE_MINBLOCKS 8   // 64 registers: measured best on C2 (4: 137 ms, 8: 113 ms, 10: 123 ms, 12: 128 ms per 8 steps); the kernel is latency-bound
+#define LF_SHADE_MINBLOCKS 7   // 72 registers.  ms of k_shade per 6 C2 steps with the llvmpipe-exact math: 6: 83.7, 7: 84.9, 8: 93.9, 9: 97.3, 10: 107.7
+                               // (profiles/r1_experiments/ab_shade_sample_ctas.txt); with the Cephes math of the earlier round 8 was best (4: 137, 8: 113, 10: 123 per 8 steps)
 #endif
 // shade, part A: hit processing + next-event estimation.  Surface hits that go on are appended to the sample queue with
 // the part of `State` DisneySample needs (5 float4 per path).
