@@ -155,6 +155,18 @@ void* lfhc_open_pack(const char* path) {
 }
 void lfhc_close(void* h) { delete static_cast<Check*>(h); }
 
+// uniforms / camera overrides (lfcuda_set_params, lfcuda_set_camera); either may be null
+void lfhc_set_params(void* h, const LfParams* p, const LfCamera* cam) {
+    Check* c = static_cast<Check*>(h);
+    if (p) c->P = *p;
+    if (cam) c->C = *cam;
+}
+void lfhc_get_params(void* h, LfParams* p, LfCamera* cam) {
+    Check* c = static_cast<Check*>(h);
+    if (p) *p = c->P;
+    if (cam) *cam = c->C;
+}
+
 void lfhc_size(void* h, int* w, int* hh) { Check* c = static_cast<Check*>(h); *w = c->P.width; *hh = c->P.height; }
 
 // accum (W*H*3, rows bottom-up like lfcuda_read_accum) += the samples of frames first, first+stride, ... in frame order

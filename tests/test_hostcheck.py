@@ -35,6 +35,8 @@ def hostcheck():
     lib.lfhc_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lfhc_render_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lfhc_render_preview.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lfhc_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lfhc_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lfhc_post_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
@@ -103,3 +105,46 @@ def test_device_source_postprocess_matches_oracle(golden_dir, oracle_lib, hostch
         out = np.empty_like(accum)
         hostcheck.lfhc_post_process(accum.ctypes.data, W, H, inv, tm, C.cast(C.byref(pp), C.c_void_p), out.ctypes.data)
         assert np.array_equal(out, post_process(accum, inv, tm, pp)), name
+
+
+EDGE_CASES = [   # (scene, LfParams overrides, LfCamera overrides): the CPU mirror of tests/test_edge_cases.py (single-tile cases)
+    ("cornell", dict(width=1, height=1, tile_width=1, tile_height=1), {}),
+    ("cornell", dict(width=37, height=23, tile_width=37, tile_height=23), {}),
+    ("cornell", dict(width=129, height=1, tile_width=129, tile_height=1), {}),
+    ("c2mini", dict(max_depth=1), {}),
+    ("c2mini", dict(max_depth=2, enable_rr=0), {}),
+    ("c3mini", dict(enable_rr=1, rr_depth=0), {}),
+    ("c3mini", dict(max_depth=8, enable_rr=0), {}),
+    ("c2mini", dict(use_envmap=0), {}),
+    ("c2mini", dict(use_constant_bg=1), {}),
+    ("cornell", {}, dict(aperture=0.02, focal_dist=0.6)),
+    ("c2mini", {}, dict(aperture=0.05, focal_dist=3.0)),
+]
+
+
+@pytest.mark.parametrize("name,params,cam", EDGE_CASES)
+def test_device_source_edge_cases(golden_dir, oracle_lib, hostcheck, name, params, cam):
+    import lavaframe_b200 as lf
+    pack, h, W, H = _open(hostcheck, golden_dir, name)
+    p, c = lf.LfParams(), lf.LfCamera()
+    hostcheck.lfhc_get_params(h, C.byref(p), C.byref(c))
+    for k, v in params.items():
+        setattr(p, k, v)
+    if params.get("use_constant_bg"):
+        p.bg_color[0], p.bg_color[1], p.bg_color[2] = 0.25, 0.5, 0.75
+    for k, v in cam.items():
+        setattr(c, k, v)
+    hostcheck.lfhc_set_params(h, C.byref(p), C.byref(c))
+    o = Oracle(pack)
+    o.update_params(**params)
+    if params.get("use_constant_bg"):
+        o.params.bg_color[0], o.params.bg_color[1], o.params.bg_color[2] = 0.25, 0.5, 0.75
+        o.update_params()
+    o.lib.lforacle_set_params(o.h, None, C.byref(c))
+    img = np.zeros((p.height, p.width, 3), np.float32)
+    assert hostcheck.lfhc_render_frames(h, 2, 2, 1, 1, img.ctypes.data) == 0
+    ref = o.render_frames(2, 2)
+    o.close()
+    hostcheck.lfhc_close(h)
+    assert ref.any() or params.get("width") == 1
+    assert np.array_equal(img, ref), f"{name} {params} {cam}: {int((img != ref).any(axis=2).sum())} pixels differ"
