@@ -163,25 +163,55 @@ def run_reference(args, workload, desc):
         "gpu_launches": 0,
     }
     if not args.no_llvmpipe:
-        line["llvmpipe_c1"] = llvmpipe_c1()
+        lp = llvmpipe_rate(workload) if workload in LLVMPIPE_SCENES else None
+        if lp and "samples_per_s_steady" in lp:
+            # the reference itself runs this workload's scene: it is the figure of this line; the oracle port's stays beside it
+            line["oracle_port"] = dict(line["cpu_baseline"])
+            v = lp["samples_per_s_steady"]
+            what = f"the unmodified reference renderer + GLSL on Mesa llvmpipe ({lp['gl']}), steady state after the shader JIT: {lp['workload']}"
+            line["value"] = v
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "reference", "sample": what}
+            line["e2e"]["value"] = v
+            line["config"]["sample"] = what
+            line["llvmpipe"] = lp
+        else:
+            line["llvmpipe_c1"] = llvmpipe_c1()
     print(json.dumps(line), flush=True)
 
 
-def llvmpipe_c1():
-    """The UNMODIFIED reference renderer + GLSL on Mesa llvmpipe, Cornell 256x256, 64 spp (C1) on this box's host cores."""
+# The reference on llvmpipe per workload: (scene generator, spp, what it is).  C3 / C4 are timed on the SAME scene at 480x270 (the
+# cost of a pixel-sample does not depend on the frame size to first order; a full 4K frame costs llvmpipe minutes per sample);
+# C2's 0.87 M-triangle mesh exceeds this llvmpipe's 65 536-texel buffer textures, so C2 has no llvmpipe figure (oracle port instead).
+LLVMPIPE_SCENES = {
+    "c1": ("cornell_256", 64, "C1 cornell_box.scene 256x256, depth 4, 64 spp"),
+    "c3_full": ("c3_small", 6, "the C3 scene at 480x270 (same instances, textures, lights), 6 spp"),
+    "c4_stress": ("c4_mini", 5, "the C4 scene (1296 instances, 20.57 M triangles, depth 8) at 480x270, 5 spp"),
+}
+
+
+def llvmpipe_rate(workload):
+    """The UNMODIFIED reference renderer + GLSL on Mesa llvmpipe on this box's host cores: steady-state samples/s (all draws after
+    the first, which pays the one-time shader JIT)."""
     from scenes import gen_scenes
     ref = os.path.join(ROOT, "oracle", "_ref", "lf_ref_llvmpipe")
+    if workload not in LLVMPIPE_SCENES:
+        return {"unavailable": f"{workload} does not fit this llvmpipe's texture-buffer limits"}
     if not os.path.exists(ref) or gen_scenes.mesa_dir() is None:
         return {"unavailable": "oracle/_ref/lf_ref_llvmpipe or the bundled Mesa libGL not present"}
+    gen, spp, what = LLVMPIPE_SCENES[workload]
     try:
-        scene = gen_scenes.cornell_256(os.path.join(ROOT, "scenes", "_gen", "cornell_256"))
-        res = subprocess.run([ref, "--scene", scene, "--spp", "64", "--out", "/tmp/lf_c1_llvmpipe.f32", "--timing-json"], env=gen_scenes.llvmpipe_env(),
-                             capture_output=True, text=True, timeout=600, check=True)
+        scene = gen_scenes.SCENES[gen](os.path.join(ROOT, "scenes", "_gen", gen))
+        res = subprocess.run([ref, "--scene", scene, "--spp", str(spp), "--out", f"/tmp/lf_{workload}_llvmpipe.f32", "--timing-json"],
+                             env=gen_scenes.llvmpipe_env(), capture_output=True, text=True, timeout=900, check=True)
         j = json.loads(res.stdout.strip().splitlines()[-1])
-        return {"kind": "reference", "workload": WORKLOADS["c1"][1], "samples_per_s_steady": j["samples_per_s_steady"], "first_step_s": j["first_step_s"],
+        return {"kind": "reference", "workload": what, "samples_per_s_steady": j["samples_per_s_steady"], "first_step_s": j["first_step_s"],
                 "render_s": j["render_s"], "cores": os.cpu_count(), "lp_num_threads": j["lp_num_threads"], "gl": j["gl_renderer"] + " / " + j["gl_version"]}
     except Exception as e:  # the reference arm must not take the bench down
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def llvmpipe_c1():
+    return llvmpipe_rate("c1")
 
 
 class _DevBuf:

@@ -335,6 +335,12 @@ def c3_mini(outdir):
     return _c3(outdir, "c3mini", (512, 256), 4, 256)
 
 
+def c3_small(outdir):
+    """The C3 scene (same 8x8 grid, meshes, materials, 1024^2 textures, lights) at 480x270: what the reference on llvmpipe is timed on
+    for the C3 baseline (a 1920x1080 frame costs it minutes per sample)."""
+    return _c3(outdir, "c3small", (480, 270), 8, 1024)
+
+
 def c3_full(outdir):
     """C3: 8x8 = 64 instances over 3 meshes + ground, 9 materials (4 textured, 1024^2 PNGs), 2 quad + 1 sphere light, 1920x1080."""
     return _c3(outdir, "c3full", (1920, 1080), 8, 1024)
@@ -402,7 +408,7 @@ def c4_mini(outdir):
 
 
 SCENES = {"cornell_256": cornell_256, "c2_mini": c2_mini, "c2_full": c2_full, "c3_mini": c3_mini, "c3_full": c3_full,
-          "c4_stress": c4_stress, "c4_mini": c4_mini, "c4_gold": c4_gold}
+          "c4_stress": c4_stress, "c4_mini": c4_mini, "c4_gold": c4_gold, "c3_small": c3_small}
 
 
 def build_pack(name, outdir):
