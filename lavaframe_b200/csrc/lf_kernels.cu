@@ -489,9 +489,61 @@ void launch_generate(const LaunchCtx& L) {
     if (L.count) k_generate<true><<<blocks, 256, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, L.counters);
     else k_generate<false><<<blocks, 256, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, L.counters);
 }
+// ---- ray-sort experiment (SortCtx in lf_kernels.h): bin = (origin cell, direction octant); histogram, scan, scatter
+struct SortGrid { float lo[3], inv[3]; };
+__global__ void __launch_bounds__(256) k_sort_keys(PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp, SortGrid G,
+                                                   unsigned* __restrict__ keys, unsigned* hist) {
+    const int count = *countp;
+    constexpr int C = 1 << kSortCellBits;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int s = queue[i];
+        const float4 o = A.ray_o[s], d = A.ray_d[s];
+        int cx = min(max((int)((o.x - G.lo[0]) * G.inv[0]), 0), C - 1);
+        int cy = min(max((int)((o.y - G.lo[1]) * G.inv[1]), 0), C - 1);
+        int cz = min(max((int)((o.z - G.lo[2]) * G.inv[2]), 0), C - 1);
+        unsigned oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+        unsigned key = ((((unsigned)cz << kSortCellBits | (unsigned)cy) << kSortCellBits | (unsigned)cx) << 3) | oct;
+        keys[i] = key;
+        atomicAdd(hist + key, 1u);
+    }
+}
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* hist) {   // exclusive scan of kSortBins counters, one CTA
+    __shared__ unsigned part[1024];
+    constexpr int PER = kSortBins / 1024;
+    unsigned local[PER], sum = 0;
+    for (int k = 0; k < PER; k++) { local[k] = hist[threadIdx.x * PER + k]; sum += local[k]; }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - sum;
+    for (int k = 0; k < PER; k++) { hist[threadIdx.x * PER + k] = run; run += local[k]; }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ queue, const int* __restrict__ countp, const unsigned* __restrict__ keys,
+                                                      unsigned* offsets, int* __restrict__ out) {
+    const int count = *countp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[atomicAdd(offsets + keys[i], 1u)] = queue[i];
+}
+
 void launch_extend(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;
-    launch_trace(L, 0, Q.active[depth & 1], Q.counts + 0 * Q.stride + depth, Q.counts + 2 * Q.stride + depth);
+    const int* queue = Q.active[depth & 1];
+    const int* countp = Q.counts + 0 * Q.stride + depth;
+    if (L.sort && depth >= 1) {      // primary rays are coherent already (8x4 pixel blocks per warp)
+        const SortCtx& S = *L.sort;
+        SortGrid G;
+        for (int k = 0; k < 3; k++) { G.lo[k] = S.lo[k]; G.inv[k] = S.inv[k]; }
+        cudaMemsetAsync(S.hist, 0, kSortBins * sizeof(unsigned), L.stream);
+        k_sort_keys<<<L.sm_count * 8, 256, 0, L.stream>>>(L.soa, queue, countp, G, S.keys, S.hist);
+        k_sort_scan<<<1, 1024, 0, L.stream>>>(S.hist);
+        k_sort_scatter<<<L.sm_count * 8, 256, 0, L.stream>>>(queue, countp, S.keys, S.hist, S.sorted);
+        queue = S.sorted;
+    }
+    launch_trace(L, 0, queue, countp, Q.counts + 2 * Q.stride + depth);
 }
 template <bool ENV, bool LIGHTS, bool TEX>
 static void launch_shade_v(const LaunchCtx& L, int depth, int blocks) {

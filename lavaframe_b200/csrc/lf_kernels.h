@@ -5,6 +5,18 @@
 
 namespace lf {
 
+// Ray-sort experiment (off unless LF_SORT_RAYS=1): the live queue of bounces >= 1 is counting-sorted by (origin cell, direction
+// octant) before the extend kernel, so that the rays a warp pulls walk similar nodes.  Only the ORDER in which slots are traced
+// changes; every ray's result lands in its own slot, so images are identical bit for bit.
+constexpr int kSortCellBits = 4;                                  // cells per axis = 16
+constexpr int kSortBins = 1 << (3 * kSortCellBits + 3);           // x 8 direction octants = 32 768 bins
+struct SortCtx {
+    int*      sorted = nullptr;     // the sorted copy of the queue (k_shade keeps reading the unsorted one: its state loads stay coalesced)
+    unsigned* keys = nullptr;       // bin of every queue entry
+    unsigned* hist = nullptr;       // kSortBins counters -> exclusive offsets
+    float lo[3] = {0, 0, 0}, inv[3] = {0, 0, 0};   // scene bounds -> cell index
+};
+
 struct LaunchCtx {
     DevScene     scene;
     DevParams    params;
@@ -16,6 +28,7 @@ struct LaunchCtx {
     int persistent_blocks;   // CTAs of the persistent traversal kernels (multiple of the SM count)
     int stack_depth;         // traversal stack entries the scene needs (<= 64)
     bool cull, count;
+    const SortCtx* sort = nullptr;   // non-null = sort the extend queue of bounces >= 1
 };
 
 void launch_generate(const LaunchCtx& L);

@@ -81,6 +81,8 @@ struct lfcuda_ctx {
     std::vector<StageEvent> events;
     LfStageStats stats{};
     uint64_t launches = 0;
+    bool sort_rays = false;               // LF_SORT_RAYS=1: ray-sort experiment (lf_kernels.h SortCtx)
+    SortCtx sort;
     int ctas_per_sm = 9;                  // CTAs per SM of the persistent traversal kernels: 9 x 128 threads x 56 registers fill the
                                           // register file exactly (measured: 8 -> 9 = -5 % extend/shadow time; 10 needs 48 registers and spills, +60 %)
 
@@ -170,6 +172,12 @@ int alloc_state(lfcuda_ctx* ctx) {
     if ((r = A((void**)&ctx->queues.active[1], cap * sizeof(int)))) return r;
     if ((r = A((void**)&ctx->queues.shadow, cap * sizeof(int)))) return r;
     if ((r = A((void**)&ctx->queues.sample, cap * sizeof(int)))) return r;
+    ctx->sort.sorted = nullptr; ctx->sort.keys = nullptr; ctx->sort.hist = nullptr;
+    if (ctx->sort_rays) {
+        if ((r = A((void**)&ctx->sort.sorted, cap * sizeof(int)))) return r;
+        if ((r = A((void**)&ctx->sort.keys, cap * sizeof(unsigned)))) return r;
+        if ((r = A((void**)&ctx->sort.hist, (size_t)kSortBins * sizeof(unsigned)))) return r;
+    }
     ctx->queues.stride = std::max(P.max_depth, 2) + 2;   // the preview engine runs at depth 2 whatever maxDepth is (TiledRenderer.cpp:532)
     if ((r = A((void**)&ctx->queues.counts, (size_t)kCountRows * ctx->queues.stride * sizeof(int)))) return r;
     ctx->accum_floats = (size_t)P.width * P.height * 3;
@@ -253,6 +261,7 @@ void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
     L.stack_depth = c->packed.stack_depth;
     L.cull = !c->params.no_cull;
     L.count = c->params.count_work != 0;
+    L.sort = (c->sort_rays && c->sort.sorted) ? &c->sort : nullptr;
 }
 
 // One batch of `nframes` (<= frames_cap) frames of one tile through the pipeline.
@@ -324,6 +333,7 @@ int lfcuda_create(lfcuda_ctx** out, int device) {
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("LF_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) c->ctas_per_sm = v; }
+    if (const char* e = getenv("LF_SORT_RAYS")) c->sort_rays = atoi(e) != 0;
     *out = c;
     return 0;
 }
@@ -398,6 +408,16 @@ int lfcuda_upload_scene(lfcuda_ctx* ctx, const LfSceneView* v) {
         rd.res.linear.devPtr = tris;
         rd.res.linear.sizeInBytes = P.tris.size() * sizeof(float4);
         if (!P.tris.empty()) CK(cudaCreateTextureObject(&D.tris_tex, &rd, &td, nullptr));
+    }
+    if (P.top_ref >= 0 && (size_t)4 * P.top_ref + 3 < P.nodes.size()) {   // scene bounds for the ray-sort grid: the root's two child boxes
+        const float4* n = P.nodes.data() + (size_t)4 * P.top_ref;
+        const float lmin[3] = {n[0].x, n[0].y, n[0].z}, lmax[3] = {n[0].w, n[1].x, n[1].y};
+        const float rmin[3] = {n[1].z, n[1].w, n[2].x}, rmax[3] = {n[2].y, n[2].z, n[2].w};
+        for (int k = 0; k < 3; k++) {
+            float lo = std::min(lmin[k], rmin[k]), hi = std::max(lmax[k], rmax[k]);
+            ctx->sort.lo[k] = lo;
+            ctx->sort.inv[k] = hi > lo ? (float)(1 << kSortCellBits) / (hi - lo) : 0.f;
+        }
     }
     D.top_ref = P.top_ref;
     D.num_lights = v->num_lights; D.num_materials = v->num_materials; D.num_instances = v->num_instances;
