@@ -491,13 +491,16 @@ void launch_generate(const LaunchCtx& L) {
 }
 // ---- ray-sort experiment (SortCtx in lf_kernels.h): bin = (origin cell, direction octant); histogram, scan, scatter
 struct SortGrid { float lo[3], inv[3]; };
+template <bool SHADOW>   // SHADOW: the slot's first NEE ray (env if requested, else the analytic light's)
 __global__ void __launch_bounds__(256) k_sort_keys(PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp, SortGrid G,
                                                    unsigned* __restrict__ keys, unsigned* hist) {
     const int count = *countp;
     constexpr int C = 1 << kSortCellBits;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const int s = queue[i];
-        const float4 o = A.ray_o[s], d = A.ray_d[s];
+        float4 o, d;
+        if (SHADOW) { o = A.sh_o[s]; d = (__float_as_int(o.w) & 1) ? A.sh_d0[s] : A.sh_d1[s]; }
+        else { o = A.ray_o[s]; d = A.ray_d[s]; }
         int cx = min(max((int)((o.x - G.lo[0]) * G.inv[0]), 0), C - 1);
         int cy = min(max((int)((o.y - G.lo[1]) * G.inv[1]), 0), C - 1);
         int cz = min(max((int)((o.z - G.lo[2]) * G.inv[2]), 0), C - 1);
@@ -529,20 +532,23 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const int* __restrict__ qu
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) out[atomicAdd(offsets + keys[i], 1u)] = queue[i];
 }
 
+template <bool SHADOW>
+static const int* sort_queue(const LaunchCtx& L, const int* queue, const int* countp) {
+    const SortCtx& S = *L.sort;
+    SortGrid G;
+    for (int k = 0; k < 3; k++) { G.lo[k] = S.lo[k]; G.inv[k] = S.inv[k]; }
+    cudaMemsetAsync(S.hist, 0, kSortBins * sizeof(unsigned), L.stream);
+    k_sort_keys<SHADOW><<<L.sm_count * 8, 256, 0, L.stream>>>(L.soa, queue, countp, G, S.keys, S.hist);
+    k_sort_scan<<<1, 1024, 0, L.stream>>>(S.hist);
+    k_sort_scatter<<<L.sm_count * 8, 256, 0, L.stream>>>(queue, countp, S.keys, S.hist, S.sorted);
+    return S.sorted;
+}
+
 void launch_extend(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;
     const int* queue = Q.active[depth & 1];
     const int* countp = Q.counts + 0 * Q.stride + depth;
-    if (L.sort && depth >= 1) {      // primary rays are coherent already (8x4 pixel blocks per warp)
-        const SortCtx& S = *L.sort;
-        SortGrid G;
-        for (int k = 0; k < 3; k++) { G.lo[k] = S.lo[k]; G.inv[k] = S.inv[k]; }
-        cudaMemsetAsync(S.hist, 0, kSortBins * sizeof(unsigned), L.stream);
-        k_sort_keys<<<L.sm_count * 8, 256, 0, L.stream>>>(L.soa, queue, countp, G, S.keys, S.hist);
-        k_sort_scan<<<1, 1024, 0, L.stream>>>(S.hist);
-        k_sort_scatter<<<L.sm_count * 8, 256, 0, L.stream>>>(queue, countp, S.keys, S.hist, S.sorted);
-        queue = S.sorted;
-    }
+    if (L.sort && (L.sort->mode & 1) && depth >= 1) queue = sort_queue<false>(L, queue, countp);   // primary rays are coherent already (8x4 pixel blocks per warp)
     launch_trace(L, 0, queue, countp, Q.counts + 2 * Q.stride + depth);
 }
 template <bool ENV, bool LIGHTS, bool TEX>
@@ -569,7 +575,10 @@ void launch_sample(const LaunchCtx& L, int depth) {
 }
 void launch_shadow(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;
-    launch_trace(L, 1, Q.shadow, Q.counts + 1 * Q.stride + depth, Q.counts + 3 * Q.stride + depth);
+    const int* queue = Q.shadow;
+    const int* countp = Q.counts + 1 * Q.stride + depth;
+    if (L.sort && (L.sort->mode & 2)) queue = sort_queue<true>(L, queue, countp);
+    launch_trace(L, 1, queue, countp, Q.counts + 3 * Q.stride + depth);
 }
 void launch_accumulate(const LaunchCtx& L, float* accum) {
     int n = L.params.tile_w * L.params.tile_h;

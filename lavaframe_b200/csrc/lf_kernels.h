@@ -5,8 +5,8 @@
 
 namespace lf {
 
-// Ray-sort experiment (off unless LF_SORT_RAYS=1): the live queue of bounces >= 1 is counting-sorted by (origin cell, direction
-// octant) before the extend kernel, so that the rays a warp pulls walk similar nodes.  Only the ORDER in which slots are traced
+// Ray-sort experiment (off unless LF_SORT_RAYS is set; bit 0 = extend queue of bounces >= 1, bit 1 = shadow queue): the queue is
+// counting-sorted by (origin cell, direction octant) before the traversal kernel, so that the rays a warp pulls walk similar nodes.  Only the ORDER in which slots are traced
 // changes; every ray's result lands in its own slot, so images are identical bit for bit.
 constexpr int kSortCellBits = 4;                                  // cells per axis = 16
 constexpr int kSortBins = 1 << (3 * kSortCellBits + 3);           // x 8 direction octants = 32 768 bins
@@ -15,6 +15,7 @@ struct SortCtx {
     unsigned* keys = nullptr;       // bin of every queue entry
     unsigned* hist = nullptr;       // kSortBins counters -> exclusive offsets
     float lo[3] = {0, 0, 0}, inv[3] = {0, 0, 0};   // scene bounds -> cell index
+    int mode = 0;                   // LF_SORT_RAYS bits
 };
 
 struct LaunchCtx {

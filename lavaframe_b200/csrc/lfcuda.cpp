@@ -81,7 +81,7 @@ struct lfcuda_ctx {
     std::vector<StageEvent> events;
     LfStageStats stats{};
     uint64_t launches = 0;
-    bool sort_rays = false;               // LF_SORT_RAYS=1: ray-sort experiment (lf_kernels.h SortCtx)
+    bool sort_rays = false;               // LF_SORT_RAYS=1|2|3: ray-sort experiment (lf_kernels.h SortCtx)
     SortCtx sort;
     int ctas_per_sm = 9;                  // CTAs per SM of the persistent traversal kernels: 9 x 128 threads x 56 registers fill the
                                           // register file exactly (measured: 8 -> 9 = -5 % extend/shadow time; 10 needs 48 registers and spills, +60 %)
@@ -333,7 +333,7 @@ int lfcuda_create(lfcuda_ctx** out, int device) {
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("LF_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) c->ctas_per_sm = v; }
-    if (const char* e = getenv("LF_SORT_RAYS")) c->sort_rays = atoi(e) != 0;
+    if (const char* e = getenv("LF_SORT_RAYS")) { c->sort.mode = atoi(e) & 3; c->sort_rays = c->sort.mode != 0; }
     *out = c;
     return 0;
 }

@@ -1,5 +1,5 @@
 """GPU tests of the experiment knobs that are OFF by default (run only with LF_TEST_EXPERIMENTS=1): an experiment may change speed,
-never a pixel.  LF_SORT_RAYS=1 (counting sort of the extend queue by origin cell and direction octant, lf_kernels.h SortCtx) was written
+never a pixel.  LF_SORT_RAYS (bit 0: counting sort of the extend queue, bit 1: of the shadow queue, by origin cell and direction octant, lf_kernels.h SortCtx) was written
 after this round's GPU budget was spent; this test is its first check and is part of the next round's first gpurun call."""
 import os
 import subprocess
@@ -29,8 +29,8 @@ pt.close()
 def test_sorted_rays_change_nothing(gpu, golden_dir, tmp_path, name):
     pack = os.path.join(golden_dir, f"{name}.lfpack")
     imgs = []
-    for sort in ("0", "1"):
+    for sort in ("0", "3"):
         out = str(tmp_path / f"{name}_{sort}.npy")
         subprocess.run([sys.executable, "-c", RENDER, pack, out], check=True, env=dict(os.environ, LF_SORT_RAYS=sort))
         imgs.append(np.load(out))
-    assert np.array_equal(imgs[0], imgs[1]), f"{name}: {int((imgs[0] != imgs[1]).any(axis=2).sum())} pixels differ with LF_SORT_RAYS=1"
+    assert np.array_equal(imgs[0], imgs[1]), f"{name}: {int((imgs[0] != imgs[1]).any(axis=2).sum())} pixels differ with LF_SORT_RAYS=3"
