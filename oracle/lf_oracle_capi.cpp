@@ -3,6 +3,9 @@
 #include <cstring>
 #include <string>
 
+#include <omp.h>
+#include <xmmintrin.h>
+
 #include "lf_oracle.h"
 #include "scenepack.h"
 
@@ -64,6 +67,19 @@ void lforacle_post_process(const float* accum, int w, int h, float inv, int tone
 }
 void lforacle_builtin_kat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int tex_w, int tex_h, int tex_l) {
     lforacle::Oracle::BuiltinKat(op, in4, n, out4, tex, tex_w, tex_h, tex_l);
+}
+// MXCSR exception flags (bit 1 = a denormal OPERAND was consumed, bit 4 = a result underflowed into the denormal range) OR-ed over the
+// OpenMP worker threads since the last reset.  llvmpipe runs with denormals flushed to zero, this oracle and the kernels do not: if neither
+// flag is ever raised by a render, that difference cannot have influenced it (tests/test_oracle_golden.py::test_no_denormals_on_the_path).
+int lforacle_fp_flags(int reset) {
+    int flags = 0;
+#pragma omp parallel reduction(| : flags)
+    {
+        unsigned csr = _mm_getcsr();
+        flags |= (int)(csr & 0x3fu);
+        if (reset) _mm_setcsr(csr & ~0x3fu);
+    }
+    return flags;
 }
 void lforacle_get_counters(void* hv, LfCounters* out) { *out = static_cast<Handle*>(hv)->oracle->counters; }
 void lforacle_reset_counters(void* hv) { std::memset(&static_cast<Handle*>(hv)->oracle->counters, 0, sizeof(LfCounters)); }

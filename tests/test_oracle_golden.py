@@ -254,3 +254,17 @@ def test_postprocess_vs_llvmpipe(golden_dir, oracle_lib):
         same = float(np.mean(out == ref))
         assert same >= (0.999 if name == "tm3_ca1_vig" else 1.0), f"{name}: {same:.6f} of the values bit-identical to llvmpipe"
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_no_denormals_on_the_path(golden_dir, oracle_lib, name):
+    """llvmpipe runs with denormals flushed to zero; the oracle and the kernels keep them.  That is the one known arithmetic
+    difference left, and it cannot matter if no denormal is ever consumed or produced: the MXCSR denormal-operand and underflow
+    flags of every OpenMP worker stay clear over a multi-sample render (also checked by hand on tiles of the full-size C2 / C4)."""
+    o = Oracle(_pack(golden_dir, name))
+    oracle_lib.lforacle_fp_flags(1)
+    o.render_frames(2, 8)
+    flags = oracle_lib.lforacle_fp_flags(0)
+    o.close()
+    assert not flags & 0x02, "a denormal operand was consumed"
+    assert not flags & 0x10, "a result underflowed into the denormal range"
