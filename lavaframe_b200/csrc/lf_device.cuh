@@ -419,7 +419,8 @@ LFD float GTR1(float NDotH, float a) {   // sampling.glsl:79-87
     if (a >= 1.0f) return (1.0f / kPI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return fdiv(a2 - 1.0f, kPI * lf_log(a2) * t);
+    // PI * log(a2) as Mesa compiles it: log(x) = log2(x) * ln 2, then the two constants of the product chain are folded
+    return fdiv(a2 - 1.0f, ((kPI * 0.693147180559945309417f) * lf_log2(a2)) * t);
 }
 LFD float GTR2(float NDotH, float a) {   // sampling.glsl:90-96
     float a2 = a * a;
@@ -592,11 +593,14 @@ LFN f3 EvalDiffuse(const Surf& s, f3 Csheen, f3 V, f3 N, f3 L, f3 H, float& pdf)
     pdf = dot(N, L) * (1.0f / kPI);
     float FL = SchlickFresnel(dot(N, L));
     float FV = SchlickFresnel(dot(N, V));
-    float FH = SchlickFresnel(dot(L, H));
     float Fss90 = dot(L, H) * dot(L, H) * s.mat.roughness;
     float Fss = mixf(1.0f, Fss90, FL) * mixf(1.0f, Fss90, FV);
     float ss = 1.f * (Fss * (1.0f / (dot(N, L) + dot(N, V)) - 0.5f) + 0.5f);
-    f3 Fsheen = FH * s.mat.sheen * Csheen;
+    // FH * sheen * Csheen with FH = SchlickFresnel(dot(L, H)) = m2 * m2 * m inlined: Mesa's opt_rebalance_tree turns the scalar product
+    // chain ((m2 * m2) * m) * sheen into (m2 * m2) * (m * sheen) (pinned against the reference's own EvalDiffuse on llvmpipe)
+    float mH = clampf(1.0f - dot(L, H), 0.0f, 1.0f);
+    float mH2 = mH * mH;
+    f3 Fsheen = ((mH2 * mH2) * (mH * s.mat.sheen)) * Csheen;
     return ((1.0f / kPI) * (ss + s.mat.subsurface) * s.mat.albedo + Fsheen) * (1.0f - s.mat.metallic);   // :112
 }
 LFD void disneyTints(const Surf& s, f3& Cspec0, f3& Csheen) {   // disney.glsl:140-145, :266-273

@@ -80,14 +80,15 @@ __device__ __forceinline__ float lf_log2_raw(float x) {
     return lf_mad(y, lf_mad(odd, z, even), logexp);
 }
 LFM float lf_exp(float x) { return lf_exp2(x * 1.44269504088896340736f); }
-// log(x) = log2(x) * ln 2 with the LG2 instruction's edge cases: +inf, 0 -> -inf, negative or NaN -> NaN
-LFM float lf_log(float x) {
+// log2 with the LG2 instruction's edge cases: +inf, 0 -> -inf, negative or NaN -> NaN; log(x) = log2(x) * ln 2
+LFM float lf_log2(float x) {
     float r = lf_log2_raw(x);
     if (x >= __int_as_float(0x7f800000)) r = __int_as_float(0x7f800000);
     if (x == 0.0f) r = __int_as_float(0xff800000);
     if (!(x >= 0.0f)) r = __int_as_float(0x7fc00000);
-    return r * 0.693147180559945309417f;
+    return r;
 }
+LFM float lf_log(float x) { return lf_log2(x) * 0.693147180559945309417f; }
 LFM float lf_pow(float x, float y) { return lf_exp2(lf_log2_raw(x) * y); }
 
 __device__ __forceinline__ float lf_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }

@@ -519,7 +519,9 @@ static float GTR1(float NDotH, float a) {   // sampling.glsl:79-87
     if (a >= 1.0f) return (1.0f / PI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return fdiv(a2 - 1.0f, PI * lfom::log(a2) * t);
+    // PI * log(a2): Mesa lowers log(x) to log2(x) * ln 2 and then folds the two constants of the product chain
+    // (opt_algebraic's reassociate_constant): (PI * ln 2) * log2(a2).  Pinned with lp_probe on the reference's own GTR1.
+    return fdiv(a2 - 1.0f, ((PI * 0.693147180559945309417f) * lfom::log2(a2)) * t);
 }
 static float GTR2(float NDotH, float a) {   // sampling.glsl:90-96
     float a2 = a * a;
@@ -670,7 +672,11 @@ static vec3 EvalDiffuse(const State& s, vec3 Csheen, vec3 V, vec3 N, vec3 L, vec
     float Fss90 = dot(L, H) * dot(L, H) * s.mat.roughness;
     float Fss = mixf(1.0f, Fss90, FL) * mixf(1.0f, Fss90, FV);
     float ss = 1.f * (Fss * (1.0f / (dot(N, L) + dot(N, V)) - 0.5f) + 0.5f);
-    vec3 Fsheen = FH * s.mat.sheen * Csheen;
+    // FH * sheen * Csheen with FH = m2 * m2 * m inlined: Mesa's opt_rebalance_tree turns the scalar product chain
+    // ((m2 * m2) * m) * sheen into (m2 * m2) * (m * sheen).  Pinned with the reference's own EvalDiffuse on llvmpipe (llvmpipe_bsdf.npz).
+    float mH = clampf(1.0f - dot(L, H), 0.0f, 1.0f);
+    float mH2 = mH * mH;
+    vec3 Fsheen = ((mH2 * mH2) * (mH * s.mat.sheen)) * Csheen;
     return ((1.0f / PI) * (ss + s.mat.subsurface) * s.mat.albedo + Fsheen) * (1.0f - s.mat.metallic);   // :112 (fork's variant)
 }
 
@@ -1198,6 +1204,42 @@ void Oracle::PostProcess(const float* accum, int W, int H, float inv, int tonema
             for (int k = 0; k < 3; k++) c[k] *= d;
         }
         out[3 * (size_t)i] = c[0]; out[3 * (size_t)i + 1] = c[1]; out[3 * (size_t)i + 2] = c[2];
+    }
+}
+
+// The reference's BSDF functions on explicit arguments (tests/golden/make_bsdf_golden.py runs the same calls on llvmpipe with the
+// reference's GLSL text).  Item layout, 9 vec4: [0] V | [1] N (= normal = ffnormal) | [2] L | [3] albedo, specular |
+// [4] metallic, roughness, subsurface, specularTint | [5] sheen, sheenTint, clearcoat, clearcoatRoughness |
+// [6] specTrans, eta, seed.z, seed.w | [7] tangent, seed.x | [8] bitangent, seed.y   (seeds are small integers stored as floats)
+void Oracle::BsdfKat(int op, const float* in, int n, float* out4) {
+    for (int i = 0; i < n; i++) {
+        const float* a = in + 36 * (size_t)i;
+        float* r = out4 + 4 * (size_t)i;
+        State s;
+        std::memset(&s, 0, sizeof s);
+        vec3 V = {a[0], a[1], a[2]}, N = {a[4], a[5], a[6]}, L = {a[8], a[9], a[10]};
+        s.mat.albedo = {a[12], a[13], a[14]}; s.mat.specular = a[15];
+        s.mat.metallic = a[16]; s.mat.roughness = a[17]; s.mat.subsurface = a[18]; s.mat.specularTint = a[19];
+        s.mat.sheen = a[20]; s.mat.sheenTint = a[21]; s.mat.clearcoat = a[22]; s.mat.clearcoatRoughness = a[23];
+        s.mat.specTrans = a[24]; s.eta = a[25];
+        s.normal = N; s.ffnormal = N;
+        s.tangent = {a[28], a[29], a[30]}; s.bitangent = {a[32], a[33], a[34]};
+        Inv g;
+        std::memset(&g, 0, sizeof g);
+        g.seed[0] = (uint32_t)a[31]; g.seed[1] = (uint32_t)a[35]; g.seed[2] = (uint32_t)a[26]; g.seed[3] = (uint32_t)a[27];
+        float pdf = 0.0f;
+        switch (op) {
+        case 0: { vec3 f = DisneyEval(s, V, N, L, pdf); r[0] = f.x; r[1] = f.y; r[2] = f.z; r[3] = pdf; break; }
+        case 1: { vec3 Ls = V3(0.0f); DisneySample(g, s, V, N, Ls, pdf); r[0] = Ls.x; r[1] = Ls.y; r[2] = Ls.z; r[3] = pdf; break; }
+        case 2: { vec3 Ls = V3(0.0f); vec3 f = DisneySample(g, s, V, N, Ls, pdf); r[0] = f.x; r[1] = f.y; r[2] = f.z; r[3] = rnd(g); break; }
+        case 3: r[0] = GTR1(a[0], a[1]); r[1] = GTR2(a[0], a[1]); r[2] = SmithG_GGX(a[0], a[1]); r[3] = DielectricFresnel(a[0], a[25]); break;
+        case 4: {
+            vec3 h1 = ImportanceSampleGTR1(a[17], a[0], a[1]), h2 = ImportanceSampleGTR2(a[17], a[0], a[1]), c = CosineSampleHemisphere(a[0], a[1]);
+            r[0] = h1.x + h1.z; r[1] = h2.x + h2.z; r[2] = c.x + c.z; r[3] = h1.y + h2.y + c.y;
+            break;
+        }
+        default: r[0] = r[1] = r[2] = r[3] = 0.0f; break;
+        }
     }
 }
 

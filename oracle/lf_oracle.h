@@ -56,6 +56,12 @@ struct Oracle {
     // llvmpipe): n vec4 arguments -> n vec4 results of expression group `op` (see the switch in lf_oracle.cpp).
     // `tex` (W x H x L RGBA8, for the texture-filter group) may be null otherwise.
     static void BuiltinKat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int texW, int texH, int texL);
+
+    // BSDF known-answer probe (tests/golden/llvmpipe_bsdf.npz, made by executing the reference's OWN disney.glsl / sampling.glsl
+    // functions on llvmpipe): n items of 9 vec4 (V, N, L, material, frame, RNG seed; layout in lf_oracle.cpp) -> n vec4.
+    // op 0: DisneyEval -> (f, pdf); 1: DisneySample -> (L, pdf); 2: DisneySample -> (f, rand() after the call);
+    // 3: (GTR1, GTR2, SmithG_GGX, DielectricFresnel) of (a.x, a.y); 4: ImportanceSampleGTR1 / GTR2 / CosineSampleHemisphere.
+    static void BsdfKat(int op, const float* in, int n, float* out4);
 };
 
 }  // namespace lforacle

@@ -65,6 +65,7 @@ void lforacle_post_process(const float* accum, int w, int h, float inv, int tone
     std::memset(&none, 0, sizeof none);
     lforacle::Oracle::PostProcess(accum, w, h, inv, tonemap_index, pp ? *pp : none, out);
 }
+void lforacle_bsdf_kat(int op, const float* in, int n, float* out4) { lforacle::Oracle::BsdfKat(op, in, n, out4); }
 void lforacle_builtin_kat(int op, const float* in4, int n, float* out4, const uint8_t* tex, int tex_w, int tex_h, int tex_l) {
     lforacle::Oracle::BuiltinKat(op, in4, n, out4, tex, tex_w, tex_h, tex_l);
 }

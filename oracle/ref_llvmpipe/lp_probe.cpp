@@ -6,7 +6,8 @@
 //   lp_probe --in args.f32 --n N --expr 'vec4(sin(a.x), cos(a.x), 0, 0)' --out res.f32
 //            [--tex8 W H L file.rgba8]      sampler2DArray tex8  (GL_RGBA8, LINEAR/LINEAR, REPEAT: Renderer.cpp:152-161)
 //            [--texf W H file.rgb32f]       sampler2D texf       (GL_RGB32F, LINEAR/LINEAR: Renderer.cpp:166-172)
-//            [--pre 'GLSL declarations']
+//            [--pre 'GLSL declarations']      inserted before main(); may call `vec4 A(int k)`
+//            [--stride K]                     K vec4 per item: `a` = A(0), the others through A(1) .. A(K-1); args.f32 then holds N*K vec4
 // args.f32 holds N vec4 (16 bytes each) = `a` in the expression; res.f32 receives N vec4.
 #include <GL/gl3w.h>
 
@@ -63,6 +64,7 @@ static GLuint compile(GLenum type, const std::string& src) {
 int main(int argc, char** argv) {
     std::string in, out = "res.f32", expr = "a", pre, tex8File, texfFile;
     long n = 0;
+    int stride = 1;
     int t8w = 0, t8h = 0, t8l = 0, tfw = 0, tfh = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -71,6 +73,7 @@ int main(int argc, char** argv) {
         else if (a == "--n") n = atol(next().c_str());
         else if (a == "--expr") expr = next();
         else if (a == "--pre") pre = next();
+        else if (a == "--stride") stride = atoi(next().c_str());
         else if (a == "--out") out = next();
         else if (a == "--tex8") { t8w = atoi(next().c_str()); t8h = atoi(next().c_str()); t8l = atoi(next().c_str()); tex8File = next(); }
         else if (a == "--texf") { tfw = atoi(next().c_str()); tfh = atoi(next().c_str()); texfFile = next(); }
@@ -78,10 +81,11 @@ int main(int argc, char** argv) {
     }
     if (in.empty() || n <= 0) { fprintf(stderr, "usage: lp_probe --in args.f32 --n N --expr E --out res.f32\n"); return 2; }
     std::vector<unsigned char> args = slurp(in);
-    if ((long)args.size() < n * 16) { fprintf(stderr, "input too short\n"); return 2; }
+    if (stride < 1 || (long)args.size() < n * 16 * stride) { fprintf(stderr, "input too short\n"); return 2; }
     const int W = 1024;
     const int H = (int)((n + W - 1) / W);
-    args.resize((size_t)W * H * 16, 0);
+    const int IW = 1024, IH = (int)((n * stride + IW - 1) / IW);       // argument texture: item i at texels [i * stride, (i + 1) * stride)
+    args.resize((size_t)IW * IH * 16, 0);
 
     void* gl = dlopen("libGL.so.1", RTLD_NOW | RTLD_GLOBAL);
     if (!gl) { fprintf(stderr, "dlopen libGL.so.1: %s\n", dlerror()); return 3; }
@@ -106,7 +110,7 @@ int main(int argc, char** argv) {
     glGenTextures(1, &inTex);
     glActiveTexture(GL_TEXTURE0);
     glBindTexture(GL_TEXTURE_2D, inTex);
-    glTexImage2D(GL_TEXTURE_2D, 0, GL_RGBA32F, W, H, 0, GL_RGBA, GL_FLOAT, args.data());
+    glTexImage2D(GL_TEXTURE_2D, 0, GL_RGBA32F, IW, IH, 0, GL_RGBA, GL_FLOAT, args.data());
     glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST);
     glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_NEAREST);
     glGenTextures(1, &outTex);
@@ -147,7 +151,9 @@ int main(int argc, char** argv) {
     const std::string vs =
         "#version 330\nvoid main() { vec2 p = vec2((gl_VertexID & 1) * 4 - 1, (gl_VertexID & 2) * 2 - 1); gl_Position = vec4(p, 0, 1); }\n";
     const std::string fs = "#version 330\nprecision highp float;\nuniform sampler2D inTex;\nuniform sampler2DArray tex8;\nuniform sampler2D texf;\n"
-                           "out vec4 res;\n" + pre + "\nvoid main() {\n  vec4 a = texelFetch(inTex, ivec2(gl_FragCoord.xy), 0);\n  res = " + expr + ";\n}\n";
+                           "out vec4 res;\n"
+                           "vec4 A(int k) { int j = (int(gl_FragCoord.y) * 1024 + int(gl_FragCoord.x)) * " + std::to_string(stride) + " + k; return texelFetch(inTex, ivec2(j % 1024, j / 1024), 0); }\n" +
+                           pre + "\nvoid main() {\n  vec4 a = A(0);\n  res = " + expr + ";\n}\n";
     GLuint prog = glCreateProgram();
     glAttachShader(prog, compile(GL_VERTEX_SHADER, vs));
     glAttachShader(prog, compile(GL_FRAGMENT_SHADER, fs));

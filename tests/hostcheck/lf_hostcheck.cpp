@@ -214,6 +214,40 @@ int lfhc_render_preview(void* h, int pv_w, int pv_h, int max_depth, int use_dof,
     return 0;
 }
 
+// The kernels' BSDF functions on explicit arguments: same item layout and ops as Oracle::BsdfKat (oracle/lf_oracle.cpp), compared by
+// tests/test_hostcheck.py with what the reference's own GLSL functions return on llvmpipe (tests/golden/llvmpipe_bsdf.npz).
+void lfhc_bsdf_kat(int op, const float* in, int n, float* out4) {
+    for (int i = 0; i < n; i++) {
+        const float* a = in + 36 * (size_t)i;
+        float* r = out4 + 4 * (size_t)i;
+        Surf s;
+        std::memset(&s, 0, sizeof s);
+        f3 V = mk3(a[0], a[1], a[2]), N = mk3(a[4], a[5], a[6]), L = mk3(a[8], a[9], a[10]);
+        s.mat.albedo = mk3(a[12], a[13], a[14]); s.mat.specular = a[15];
+        s.mat.metallic = a[16]; s.mat.roughness = a[17]; s.mat.subsurface = a[18]; s.mat.specularTint = a[19];
+        s.mat.sheen = a[20]; s.mat.sheenTint = a[21]; s.mat.clearcoat = a[22]; s.mat.clearcoatRoughness = a[23];
+        s.mat.specTrans = a[24]; s.eta = a[25];
+        s.normal = N; s.ffnormal = N;
+        s.tangent = mk3(a[28], a[29], a[30]); s.bitangent = mk3(a[32], a[33], a[34]);
+        Rng g;
+        g.x = (unsigned)a[31]; g.y = (unsigned)a[35]; g.z = (unsigned)a[26]; g.w = (unsigned)a[27];
+        float pdf = 0.0f;
+        r[0] = r[1] = r[2] = r[3] = 0.0f;
+        switch (op) {
+        case 0: { f3 f = DisneyEval(s, V, N, L, pdf); r[0] = f.x; r[1] = f.y; r[2] = f.z; r[3] = pdf; break; }
+        case 1: { f3 Ls = mk3(0.0f); DisneySample(s, V, N, g, Ls, pdf); r[0] = Ls.x; r[1] = Ls.y; r[2] = Ls.z; r[3] = pdf; break; }
+        case 2: { f3 Ls = mk3(0.0f); f3 f = DisneySample(s, V, N, g, Ls, pdf); r[0] = f.x; r[1] = f.y; r[2] = f.z; r[3] = rnd(g); break; }
+        case 3: r[0] = GTR1(a[0], a[1]); r[1] = GTR2(a[0], a[1]); r[2] = SmithG_GGX(a[0], a[1]); r[3] = DielectricFresnel(a[0], a[25]); break;
+        case 4: {
+            f3 h1 = ImportanceSampleGTR1(a[17], a[0]), h2 = ImportanceSampleGTR2(a[17], a[0], a[1]), c = CosineSampleHemisphere(a[0], a[1]);
+            r[0] = h1.x + h1.z; r[1] = h2.x + h2.z; r[2] = c.x + c.z; r[3] = h1.y + h2.y + c.y;
+            break;
+        }
+        default: break;
+        }
+    }
+}
+
 // k_post for a W x H accumulation buffer
 void lfhc_post_process(const float* accum, int W, int H, float inv, int tonemap, const LfPostParams* pp, float* out) {
     LfPostParams p;

@@ -37,6 +37,7 @@ def load_oracle():
     lib.lforacle_primary_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lforacle_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lforacle_rand_kat.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.lforacle_bsdf_kat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.lforacle_fp_flags.restype = C.c_int
     lib.lforacle_fp_flags.argtypes = [C.c_int]
     lib.lforacle_post_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
@@ -135,4 +136,14 @@ def post_process(accum, inv, tonemap_index, post=None):
     out = np.empty_like(a)
     lib.lforacle_post_process(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], float(inv), int(tonemap_index),
                               C.cast(C.byref(post), C.c_void_p) if post is not None else None, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def bsdf_kat(op, items):
+    """The oracle's DisneyEval / DisneySample / microfacet helpers on (n, 9, 4) float32 items (layout: lf_oracle.cpp BsdfKat)."""
+    lib = load_oracle()
+    a = np.ascontiguousarray(items, np.float32)
+    assert a.ndim == 3 and a.shape[1:] == (9, 4)
+    out = np.empty((a.shape[0], 4), np.float32)
+    lib.lforacle_bsdf_kat(op, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p))
     return out

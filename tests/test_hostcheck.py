@@ -37,6 +37,7 @@ def hostcheck():
     lib.lfhc_render_preview.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.lfhc_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lfhc_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lfhc_bsdf_kat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.lfhc_post_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     return lib
 
@@ -148,3 +149,19 @@ def test_device_source_edge_cases(golden_dir, oracle_lib, hostcheck, name, param
     hostcheck.lfhc_close(h)
     assert ref.any() or params.get("width") == 1
     assert np.array_equal(img, ref), f"{name} {params} {cam}: {int((img != ref).any(axis=2).sum())} pixels differ"
+
+
+BSDF_OPS = ["DisneyEval (f, pdf)", "DisneySample (L, pdf)", "DisneySample (f, next rand())", "GTR1 GTR2 SmithG_GGX DielectricFresnel", "importance samplers"]
+
+
+@pytest.mark.parametrize("op", range(5))
+def test_device_source_bsdf_vs_llvmpipe(golden_dir, hostcheck, op):
+    """The kernels' BSDF functions against the reference's OWN disney.glsl / sampling.glsl functions executed on llvmpipe
+    (tests/golden/make_bsdf_golden.py): 2048 seeded random parameter sets per group, every value bit for bit."""
+    g = np.load(os.path.join(golden_dir, "llvmpipe_bsdf.npz"))
+    a = np.ascontiguousarray(g[f"in{op}"], np.float32)
+    ref = g[f"out{op}"]
+    out = np.empty_like(ref)
+    hostcheck.lfhc_bsdf_kat(op, a.ctypes.data, a.shape[0], out.ctypes.data)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref)) | ((out == 0) & (ref == 0))
+    assert same.all(), f"{BSDF_OPS[op]}: {int((~same.all(axis=1)).sum())} of {same.shape[0]} items differ from llvmpipe"

@@ -87,6 +87,19 @@ def test_builtins_bit_exact(golden_dir, oracle_lib, group):
     assert same.all(), f"{g['expr'][group]}: {int((~same).sum())} of {same.size} values differ from llvmpipe"
 
 
+@pytest.mark.parametrize("op", range(5))
+def test_bsdf_functions_bit_exact(golden_dir, oracle_lib, op):
+    """The oracle's DisneyEval / DisneySample / microfacet helpers / importance samplers against the reference's OWN GLSL functions
+    executed on llvmpipe with random parameters (tests/golden/make_bsdf_golden.py): pins what Mesa's compiler does to each expression
+    (constant folding across `PI * log(a2)`, the rebalanced `FH * sheen` product ...) for every lobe and parameter, not only those
+    a golden scene happens to use."""
+    from oracle_api import bsdf_kat
+    g = np.load(os.path.join(golden_dir, "llvmpipe_bsdf.npz"))
+    out = bsdf_kat(op, g[f"in{op}"])
+    same = _same_bits(out, g[f"out{op}"])
+    assert same.all(), f"op {op}: {int((~same.all(axis=1)).sum())} of {same.shape[0]} items differ from llvmpipe"
+
+
 def test_cornell_pack_matches_reference_dump(golden_dir):
     """SURVEY.md Appendix A KAT: the flattened Cornell arrays as the reference's own host code builds them."""
     p = ScenePack(_pack(golden_dir, "cornell"))

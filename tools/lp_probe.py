@@ -18,15 +18,19 @@ PROBE = os.path.join(ROOT, "oracle", "_ref", "lp_probe")
 
 
 def glsl(expr, a, pre="", tex8=None, texf=None):
+    """a: (N,) or (N, 4) -> `a`; or (N, K, 4): K vec4 per item, read in the shader with A(0) .. A(K-1)."""
     a = np.ascontiguousarray(a, np.float32)
     if a.ndim == 1:
         a = np.stack([a, np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)], axis=1)
     n = a.shape[0]
+    stride = a.shape[1] if a.ndim == 3 else 1
     with tempfile.TemporaryDirectory() as tmp:
         a.tofile(os.path.join(tmp, "in.f32"))
         cmd = [PROBE, "--in", os.path.join(tmp, "in.f32"), "--n", str(n), "--expr", expr, "--out", os.path.join(tmp, "out.f32")]
         if pre:
             cmd += ["--pre", pre]
+        if stride > 1:
+            cmd += ["--stride", str(stride)]
         if tex8 is not None:                         # (L, H, W, 4) uint8
             t = np.ascontiguousarray(tex8, np.uint8)
             t.tofile(os.path.join(tmp, "t8.bin"))
