@@ -10,6 +10,7 @@
 // Xlib (fakex11.c) — see SURVEY.md Appendix H.
 //
 //   lf_ref_llvmpipe --scene S --spp N --out img.f32 [--probe hits] [--timing-json]
+//                   [--bg R G B]   (renderOptions.useConstantBg + bgColor, UI-only in the reference: Main.cpp:504-507)
 //                   [--tonemap I] [--vignette INTENSITY POWER] [--ca DISTORTION(0|1) DISTANCE P1 P2 P3]   (RenderOptions the UI sets, Main.cpp:470-500)
 //   lf_ref_llvmpipe --extract-assets DIR        (writes the reference's build_include/assets tree)
 //
@@ -108,6 +109,8 @@ int main(int argc, char** argv) {
     bool timingJson = false, previewDof = false;
     float previewScale = 0.f;                        // > 0: render the preview engine's image instead (--preview SCALE)
     int tonemap = 0;
+    bool constantBg = false;
+    float bg[3] = {0.5f, 0.5f, 0.5f};
     bool useVignette = false, useCA = false, caDistortion = false;
     float vigI = 0.f, vigP = 1.f, caDist = 0.05f, caP1 = 5.f, caP2 = -0.5f, caP3 = 0.5f;
     for (int i = 1; i < argc; i++) {
@@ -123,6 +126,7 @@ int main(int argc, char** argv) {
         else if (a == "--preview") previewScale = (float)atof(next().c_str());
         else if (a == "--preview-dof") previewDof = true;
         else if (a == "--tonemap") tonemap = atoi(next().c_str());
+        else if (a == "--bg") { constantBg = true; for (int k = 0; k < 3; k++) bg[k] = (float)atof(next().c_str()); }
         else if (a == "--vignette") { useVignette = true; vigI = (float)atof(next().c_str()); vigP = (float)atof(next().c_str()); }
         else if (a == "--ca") {
             useCA = true; caDistortion = atoi(next().c_str()) != 0; caDist = (float)atof(next().c_str());
@@ -197,6 +201,7 @@ int main(int argc, char** argv) {
     if (!LoadSceneFromFile(sceneFile, GlobalState.scene, ro)) return 4;
     double tLoad1 = now();
     ro.tonemapIndex = tonemap;
+    if (constantBg) { ro.useConstantBg = true; ro.bgColor = Vec3(bg[0], bg[1], bg[2]); }
     ro.useVignette = useVignette; ro.vignetteIntensity = vigI; ro.vignettePower = vigP;
     ro.useCA = useCA; ro.useCADistortion = caDistortion; ro.caDistance = caDist; ro.caP1 = caP1; ro.caP2 = caP2; ro.caP3 = caP3;
     GlobalState.scene->renderOptions = ro;          // Main.cpp:969
