@@ -232,6 +232,8 @@ def test_tiled_render_vs_llvmpipe(golden_dir, oracle_lib):
     img = acc / np.float32(n)
     assert radiance_agreement(img, g["sppN"]) >= 0.999
     assert rmse_over_mean_luminance(img, g["sppN"]) < 0.005
+    bits = float(np.mean((img == g["sppN"]).all(axis=2)))
+    assert bits >= 0.9999, f"tiled render bit-identical to the reference on {bits:.6f} of pixels"
 
 
 def _post_cases(golden_dir):
