@@ -104,7 +104,7 @@ static double now() {
 }
 
 int main(int argc, char** argv) {
-    std::string sceneFile, out = "out.f32", probe, extractDir, shadersOverride;
+    std::string sceneFile, out = "out.f32", out8, probe, extractDir, shadersOverride;
     int spp = 1;
     bool timingJson = false, previewDof = false;
     float previewScale = 0.f;                        // > 0: render the preview engine's image instead (--preview SCALE)
@@ -119,6 +119,7 @@ int main(int argc, char** argv) {
         if (a == "--scene") sceneFile = next();
         else if (a == "--spp") spp = atoi(next().c_str());
         else if (a == "--out") out = next();
+        else if (a == "--out8") out8 = next();          // also GetOutputBuffer (8-bit RGB, what SaveFrame* of Export.h write)
         else if (a == "--probe") probe = next();
         else if (a == "--extract-assets") extractDir = next();
         else if (a == "--shaders") shadersOverride = next();
@@ -261,6 +262,17 @@ int main(int argc, char** argv) {
     if (!f) { perror(out.c_str()); return 6; }
     fwrite(img, sizeof(float), (size_t)w * h * 3, f);
     fclose(f);
+
+    if (!out8.empty()) {
+        unsigned char* img8 = nullptr;
+        int w8 = 0, h8 = 0;
+        r->GetOutputBuffer(&img8, w8, h8);
+        FILE* f8 = fopen(out8.c_str(), "wb");
+        if (!f8) { perror(out8.c_str()); return 6; }
+        fwrite(img8, 1, (size_t)w8 * h8 * 3, f8);
+        fclose(f8);
+        delete[] img8;
+    }
 
     double sum[3] = {0, 0, 0};
     long nan = 0;

@@ -93,11 +93,15 @@ def post_goldens(spp=4):
         scene = gen_scenes.cornell_256(os.path.join(tmp, "assets"), res=(64, 64))
         arrays = {"nspp": np.int32(spp)}
 
-        def run(extra):
+        def run(extra, u8=None):
             out = os.path.join(tmp, "o.f32")
-            res = subprocess.run([REFBIN, "--scene", scene, "--spp", str(spp), "--out", out, "--timing-json"] + extra,
-                                 env=gen_scenes.llvmpipe_env(), check=True, capture_output=True, text=True)
+            cmd = [REFBIN, "--scene", scene, "--spp", str(spp), "--out", out, "--timing-json"] + extra
+            if u8:
+                cmd += ["--out8", os.path.join(tmp, "o.u8")]
+            res = subprocess.run(cmd, env=gen_scenes.llvmpipe_env(), check=True, capture_output=True, text=True)
             info = json.loads(res.stdout.strip().splitlines()[-1])
+            if u8:   # GetOutputBuffer: the 8-bit RGB image SaveFrame / SaveFrameJPG / ... of Export.h write
+                arrays[u8] = np.fromfile(os.path.join(tmp, "o.u8"), np.uint8).reshape(info["height"], info["width"], 3)
             return np.fromfile(out, np.float32).reshape(info["height"], info["width"], 3)
 
         arrays["tm0"] = run([])
@@ -107,7 +111,7 @@ def post_goldens(spp=4):
                 extra += ["--vignette", str(vig[0]), str(vig[1])]
             if ca:
                 extra += ["--ca"] + [str(v) for v in ca]
-            arrays[name] = run(extra)
+            arrays[name] = run(extra, u8=f"{name}_u8" if name in ("tm2", "tm5") else None)
             print("post", name, arrays[name].mean(axis=(0, 1)))
         np.savez_compressed(os.path.join(GOLD, "cornell64_llvmpipe_post.npz"), **arrays)
 

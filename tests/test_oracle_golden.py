@@ -272,6 +272,12 @@ def test_postprocess_vs_llvmpipe(golden_dir, oracle_lib):
         same = float(np.mean(out == ref))
         assert same >= (0.999 if name == "tm3_ca1_vig" else 1.0), f"{name}: {same:.6f} of the values bit-identical to llvmpipe"
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-7)
+    # GetOutputBuffer (the 8-bit image the exporters of Export.h write) = round-to-nearest-even of clamp(colour, 0, 1) * 255
+    g = np.load(os.path.join(golden_dir, "cornell64_llvmpipe_post.npz"))
+    for name, tm, pp, ref in cases:
+        if f"{name}_u8" in g:
+            u8 = np.rint(np.clip(post_process(accum, inv, tm, pp), 0, 1) * np.float32(255)).astype(np.uint8)
+            assert np.array_equal(u8, g[f"{name}_u8"]), f"{name}: 8-bit output differs from the reference's GetOutputBuffer"
 
 
 @pytest.mark.parametrize("name", SCENES)
