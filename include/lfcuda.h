@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LFCUDA_ABI_VERSION 1
+#define LFCUDA_ABI_VERSION 2
 
 enum {
     LFCUDA_OK = 0,
@@ -188,8 +188,10 @@ int  lfcuda_render_frames(lfcuda_ctx* ctx, int32_t first_frame, int32_t nframes,
  * accumulated.  Always runs the wavefront kernels.  Asynchronous on the context's stream. */
 int  lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, int32_t max_depth, int32_t use_dof);
 /* The preview target through the post-process pass with invSampleCounter = 1, as Present()/SetViewport() display it
- * (TiledRenderer.cpp:361-364,558-562): pv_width * pv_height * 3 floats, rows bottom-up.  Synchronises the stream. */
-int  lfcuda_read_preview(lfcuda_ctx* ctx, int32_t tonemap_index, float* rgb_out);
+ * (TiledRenderer.cpp:361-364,558-562): pv_width * pv_height * 3 floats, rows bottom-up.  is_in_preview = the postShader
+ * uniform isInPreview (TiledRenderer.cpp:541: camera->isMoving): non-zero skips the chromatic-aberration branch
+ * (postprocess.glsl:128-132).  Synchronises the stream. */
+int  lfcuda_read_preview(lfcuda_ctx* ctx, int32_t tonemap_index, int32_t is_in_preview, float* rgb_out);
 /* Copy the accumulation buffer (running SUM, W*H*3 floats, rows bottom-up like glGetTexImage,
  * TiledRenderer.cpp:399-414) to host memory.  Synchronises the stream. */
 int  lfcuda_read_accum(lfcuda_ctx* ctx, float* rgb_out);

@@ -87,7 +87,7 @@ LFCUDA_SYMBOLS = {
     "lfcuda_clear": (C.c_int, [C.c_void_p]),
     "lfcuda_render_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "lfcuda_render_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
-    "lfcuda_read_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "lfcuda_read_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "lfcuda_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lfcuda_read_output": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
     "lfcuda_read_output_u8": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
@@ -126,7 +126,7 @@ def load_lfcuda():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.lfcuda_abi_version() != 1:
+    if lib.lfcuda_abi_version() != 2:
         raise LfCudaError("liblfcuda.so ABI version mismatch")
     _lfcuda = lib
     return lib

@@ -146,14 +146,27 @@ LFD float RectIntersect(f3 pos, f3 u, f3 v, f3 n, float planeW, const Ray& r) { 
     return kINF;
 }
 // intersection.glsl:53-67 with invdir hoisted out (same quotient every call); also returns the entry distance.
-LFD float AABBIntersect(f3 mn, f3 mx, f3 o, f3 invdir, float& entry) {
+// GLSL min / max on llvmpipe are MINPS / MAXPS: (a < b ? a : b), i.e. the SECOND operand whenever one is NaN, whereas the
+// GPU's FMNMX (fminf / fmaxf) returns the non-NaN one.  A slab product is NaN only as 0 * inf: a direction component that is
+// exactly 0 (1/d = inf) with the origin exactly on that face's plane.  `axisRay` (any component of invdir infinite, kept per
+// ray in Walk::axis) selects the operand-exact form; every other ray has no NaN and the two forms agree on every value the
+// caller looks at (they differ only in the sign of a zero, which no comparison here sees), so it keeps the 1-instruction
+// min / max.  KAT: tests/test_edge_cases.py::test_axis_ray_on_flat_box_plane.
+LFD float AABBIntersect(f3 mn, f3 mx, f3 o, f3 invdir, bool axisRay, float& entry) {
     f3 f = (mx - o) * invdir;
     f3 n = (mn - o) * invdir;
-    float t1 = fminf(fmaxf(f.x, n.x), fminf(fmaxf(f.y, n.y), fmaxf(f.z, n.z)));
-    float t0 = fmaxf(fminf(f.x, n.x), fmaxf(fminf(f.y, n.y), fminf(f.z, n.z)));
+    float t1, t0;
+    if (axisRay) {
+        t1 = gmin(gmax(f.x, n.x), gmin(gmax(f.y, n.y), gmax(f.z, n.z)));
+        t0 = gmax(gmin(f.x, n.x), gmax(gmin(f.y, n.y), gmin(f.z, n.z)));
+    } else {
+        t1 = fminf(fmaxf(f.x, n.x), fminf(fmaxf(f.y, n.y), fmaxf(f.z, n.z)));
+        t0 = fmaxf(fminf(f.x, n.x), fmaxf(fminf(f.y, n.y), fminf(f.z, n.z)));
+    }
     entry = t0;
     return (t1 >= t0) ? (t0 > 0.f ? t0 : t1) : -1.0f;
 }
+LFD bool has_inf(f3 v) { return fabsf(v.x) == __int_as_float(0x7f800000) || fabsf(v.y) == __int_as_float(0x7f800000) || fabsf(v.z) == __int_as_float(0x7f800000); }
 
 struct LightRec {              // 7 float4, see lf_repack.cpp
     f3 position, emission, u, v, normal, uu, vv;
@@ -185,6 +198,7 @@ struct Walk {                  // traversal registers of one ray
     int ref, sp;               // current node reference, stack pointer
     int curInst, curMat;
     bool inBlas;
+    bool axis;                 // some component of idir is infinite: AABBIntersect takes its NaN-exact form
 };
 
 LFD void hit_clear(Hit& hit) { hit.light = -1; hit.tri = -1; hit.inst = -1; hit.mat = -1; hit.u = hit.v = 0.f; hit.lpdf = 0.f; hit.t = kINF; }
@@ -229,6 +243,7 @@ LFD void walk_begin(const DevScene& S, const Ray& r, Walk& w, int* stk) {
     w.curInst = -1; w.curMat = 0;
     w.o = r.o; w.d = r.d;
     w.idir = mk3(1.0f) / r.d;
+    w.axis = has_inf(w.idir);
 }
 
 // inverse(M) * vec4(origin, 1) and * vec4(direction, 0), summed column by column like the GLSL mat4*vec4 (closest_hit.glsl:159-160)
@@ -262,8 +277,8 @@ LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, int* s
         float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3);
 #endif
         float le, re;
-        float leftHit = AABBIntersect(mk3(n0.x, n0.y, n0.z), mk3(n0.w, n1.x, n1.y), w.o, w.idir, le);
-        float rightHit = AABBIntersect(mk3(n1.z, n1.w, n2.x), mk3(n2.y, n2.z, n2.w), w.o, w.idir, re);
+        float leftHit = AABBIntersect(mk3(n0.x, n0.y, n0.z), mk3(n0.w, n1.x, n1.y), w.o, w.idir, w.axis, le);
+        float rightHit = AABBIntersect(mk3(n1.z, n1.w, n2.x), mk3(n2.y, n2.z, n2.w), w.o, w.idir, w.axis, re);
         int leftRef = __float_as_int(n3.x), rightRef = __float_as_int(n3.y);
         bool lok = leftHit > 0.0f, rok = rightHit > 0.0f;
         if (CULL) {
@@ -284,6 +299,7 @@ LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, int* s
         if (!w.inBlas) return false;
         w.inBlas = false;
         w.o = r.o; w.d = r.d; w.idir = mk3(1.0f) / r.d;
+        w.axis = has_inf(w.idir);
         w.ref = stk[(--w.sp) * kBlockThreads];
         return true;
     }
@@ -294,6 +310,7 @@ LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, int* s
     float4 r0 = ldg4(ip), r1 = ldg4(ip + 1), r2 = ldg4(ip + 2), meta = ldg4(ip + 3);
     to_instance(r0, r1, r2, r, w.o, w.d);
     w.idir = mk3(1.0f) / w.d;
+    w.axis = has_inf(w.idir);
     stk[(w.sp++) * kBlockThreads] = kRefSentinel;
     w.inBlas = true;
     w.curMat = __float_as_int(meta.y);

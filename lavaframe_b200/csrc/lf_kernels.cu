@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
     float maxDist = 0.f;
     int shMask = 0, shPhase = 0;                        // shadow: requested rays (bit 0 env, bit 1 light), ray being traced
     f3 Li = mk3(0.0f);
-    w.ref = kRefSentinel; w.sp = 0; w.inBlas = false; w.curInst = -1; w.curMat = 0;
+    w.ref = kRefSentinel; w.sp = 0; w.inBlas = false; w.axis = false; w.curInst = -1; w.curMat = 0;
     w.o = w.d = w.idir = mk3(0.f);
     hit_clear(hit);
 
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                     Ray r = world_ray();
                     w.o = r.o; w.d = r.d;
                     w.idir = mk3(wr[6 * kBlockThreads], wr[7 * kBlockThreads], wr[8 * kBlockThreads]);
+                    w.axis = has_inf(w.idir);
                     w.ref = stk[(--w.sp) * kBlockThreads];
                 }
             } else {

@@ -8,8 +8,10 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,6 +35,9 @@ struct Nccl {
     void* lib = nullptr;
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -67,7 +72,10 @@ struct lfcuda_ctx {
     // path state
     size_t capacity = 0;                  // slots
     int frames_cap = 0, slots_per_frame = 0, pix_w8 = 0, pix_h4 = 0;
-    std::vector<void*> state_allocs;
+    std::vector<void*> state_allocs, frame_allocs;
+    int state_tile_w = 0, state_tile_h = 0, state_frames_req = 0;   // what the path state was last sized for
+    int frame_w = 0, frame_h = 0;                                   // ... and the accumulation / output buffers
+    int counts_cap = 0;
     PathSoA soa{};
     Queues queues{};
     float* d_accum = nullptr; size_t accum_floats = 0;
@@ -86,8 +94,7 @@ struct lfcuda_ctx {
     int ctas_per_sm = 9;                  // CTAs per SM of the persistent traversal kernels: 9 x 128 threads x 56 registers fill the
                                           // register file exactly (measured: 8 -> 9 = -5 % extend/shadow time; 10 needs 48 registers and spills, +60 %)
 
-    // NCCL
-    Nccl nccl;
+    // NCCL (function table: process-wide g_nccl)
     void* comm = nullptr;
 };
 
@@ -133,59 +140,120 @@ void free_scene(lfcuda_ctx* c) {
     c->have_scene = false;
 }
 
+// Device memory of a context comes in three independent groups, so that changing one render parameter never disturbs what
+// another group holds (the reference changes maxDepth / tile uniforms without touching accumTexture, TiledRenderer.cpp:505-521):
+//   frame   accumulation buffer + post-process outputs          re-created (and zeroed) only when width / height change
+//   state   wavefront path state + queues                       re-created when the tile size or frames_in_flight change
+//   counts  per-bounce queue counters                           grown when max_depth grows
+void free_group(std::vector<void*>& g) {
+    for (void* p : g) cudaFree(p);
+    g.clear();
+}
 void free_state(lfcuda_ctx* c) {
-    for (void* p : c->state_allocs) cudaFree(p);
-    c->state_allocs.clear();
+    free_group(c->state_allocs);
     c->capacity = 0;
-    c->d_accum = nullptr; c->d_out_f = nullptr; c->d_out_u8 = nullptr;
+    c->soa = PathSoA{};
+    c->queues.active[0] = c->queues.active[1] = c->queues.shadow = c->queues.sample = nullptr;
+    c->sort.sorted = nullptr; c->sort.keys = nullptr; c->sort.hist = nullptr;
+}
+void free_frame(lfcuda_ctx* c) {
+    free_group(c->frame_allocs);
+    c->d_accum = nullptr; c->d_out_f = nullptr; c->d_out_u8 = nullptr; c->accum_floats = 0;
     c->d_preview = nullptr; c->d_preview_out = nullptr; c->preview_cap = 0; c->preview_w = c->preview_h = 0;
 }
 
-int alloc_state(lfcuda_ctx* ctx) {
-    free_state(ctx);
-    const LfParams& P = ctx->params;
-    ctx->pix_w8 = (P.tile_width + 7) / 8 * 8;
-    ctx->pix_h4 = (P.tile_height + 3) / 4 * 4;
-    ctx->slots_per_frame = ctx->pix_w8 * ctx->pix_h4;
-    int F = P.frames_in_flight;
-    if (F <= 0) {   // auto: about 32 M pixel-samples in flight (11 GB of path state of 180 GB), at least one frame.  Measured on C2:
-                    // 4 M -> 328, 8 M -> 360, 16 M -> 377 M samples/s with the first kernels, 16 M -> 427, 32 M -> 435, 64 M -> 436 with
-                    // the final ones: deep bounces keep enough rays to fill the persistent grid.
-        F = (int)((size_t)(32u << 20) / (size_t)ctx->slots_per_frame);
-        if (F < 1) F = 1;
-        if (F > 256) F = 256;
-    }
-    ctx->frames_cap = F;
-    size_t cap = (size_t)F * ctx->slots_per_frame;
+int alloc_frame(lfcuda_ctx* ctx, int width, int height) {
+    free_frame(ctx);
+    ctx->frame_w = ctx->frame_h = 0;
+    const size_t n = (size_t)width * height * 3;
     auto A = [&](void** p, size_t bytes) -> int {
         CK(cudaMalloc(p, bytes));
-        ctx->state_allocs.push_back(*p);
+        ctx->frame_allocs.push_back(*p);
         return 0;
     };
-    float4** f4s[] = {&ctx->soa.ray_o, &ctx->soa.ray_d, &ctx->soa.hit_f, &ctx->soa.hit_p, &ctx->soa.thr, &ctx->soa.rad, &ctx->soa.absn,
-                      &ctx->soa.stale, &ctx->soa.sf0, &ctx->soa.sf1, &ctx->soa.sf2, &ctx->soa.sf3, &ctx->soa.sf4, &ctx->soa.sh_o, &ctx->soa.sh_d0, &ctx->soa.sh_c0, &ctx->soa.sh_d1, &ctx->soa.sh_c1, &ctx->soa.sh_T};
-    for (float4** p : f4s) { int r = A((void**)p, cap * sizeof(float4)); if (r) return r; }
     int r;
-    if ((r = A((void**)&ctx->soa.hit_i, cap * sizeof(int4)))) return r;
-    if ((r = A((void**)&ctx->soa.rng, cap * sizeof(uint4)))) return r;
-    if ((r = A((void**)&ctx->queues.active[0], cap * sizeof(int)))) return r;
-    if ((r = A((void**)&ctx->queues.active[1], cap * sizeof(int)))) return r;
-    if ((r = A((void**)&ctx->queues.shadow, cap * sizeof(int)))) return r;
-    if ((r = A((void**)&ctx->queues.sample, cap * sizeof(int)))) return r;
-    ctx->sort.sorted = nullptr; ctx->sort.keys = nullptr; ctx->sort.hist = nullptr;
-    if (ctx->sort_rays) {
-        if ((r = A((void**)&ctx->sort.sorted, cap * sizeof(int)))) return r;
-        if ((r = A((void**)&ctx->sort.keys, cap * sizeof(unsigned)))) return r;
-        if ((r = A((void**)&ctx->sort.hist, (size_t)kSortBins * sizeof(unsigned)))) return r;
+    if ((r = A((void**)&ctx->d_accum, n * sizeof(float))) || (r = A((void**)&ctx->d_out_f, n * sizeof(float))) || (r = A((void**)&ctx->d_out_u8, n))) {
+        free_frame(ctx);
+        return r;
     }
-    ctx->queues.stride = std::max(P.max_depth, 2) + 2;   // the preview engine runs at depth 2 whatever maxDepth is (TiledRenderer.cpp:532)
-    if ((r = A((void**)&ctx->queues.counts, (size_t)kCountRows * ctx->queues.stride * sizeof(int)))) return r;
-    ctx->accum_floats = (size_t)P.width * P.height * 3;
-    if ((r = A((void**)&ctx->d_accum, ctx->accum_floats * sizeof(float)))) return r;
-    if ((r = A((void**)&ctx->d_out_f, ctx->accum_floats * sizeof(float)))) return r;
-    if ((r = A((void**)&ctx->d_out_u8, ctx->accum_floats))) return r;
-    CK(cudaMemsetAsync(ctx->d_accum, 0, ctx->accum_floats * sizeof(float), ctx->stream));
-    ctx->capacity = cap;
+    ctx->accum_floats = n;
+    CK(cudaMemsetAsync(ctx->d_accum, 0, n * sizeof(float), ctx->stream));
+    ctx->frame_w = width; ctx->frame_h = height;
+    return 0;
+}
+
+int ensure_counts(lfcuda_ctx* ctx, int max_depth) {
+    const int stride = std::max(max_depth, 2) + 2;   // the preview engine runs at depth 2 whatever maxDepth is (TiledRenderer.cpp:532)
+    if (ctx->queues.counts && stride <= ctx->counts_cap) { ctx->queues.stride = stride; return 0; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->queues.counts) cudaFree(ctx->queues.counts);
+    ctx->queues.counts = nullptr; ctx->counts_cap = 0;
+    CK(cudaMalloc((void**)&ctx->queues.counts, (size_t)kCountRows * stride * sizeof(int)));
+    ctx->counts_cap = stride;
+    ctx->queues.stride = stride;
+    return 0;
+}
+
+constexpr size_t kAutoSlots = (size_t)32 << 20;   // auto batch: about 32 M pixel-samples in flight.  Measured on C2: 4 M -> 328, 8 M -> 360,
+                                                  // 16 M -> 377 M samples/s with the first kernels, 16 M -> 427, 32 M -> 435, 64 M -> 436 with
+                                                  // the final ones: deep bounces keep enough rays to fill the persistent grid.
+
+// Path state for tiles of tile_w x tile_h pixels, `frames_req` frames per batch (0 = auto).  The auto batch is clamped to half of the
+// device memory that is free right now, and an allocation failure retries with half the frames (a GPU shared with torch / NCCL buffers
+// degrades instead of failing); an explicit frames_in_flight is honoured or refused.
+int alloc_state(lfcuda_ctx* ctx, int tile_w, int tile_h, int frames_req) {
+    free_state(ctx);
+    ctx->state_tile_w = ctx->state_tile_h = 0;
+    ctx->pix_w8 = (tile_w + 7) / 8 * 8;
+    ctx->pix_h4 = (tile_h + 3) / 4 * 4;
+    const size_t spf = (size_t)ctx->pix_w8 * ctx->pix_h4;
+    if (spf > (size_t)INT_MAX) return fail(ctx, LFCUDA_ELIMIT, "a tile of %d x %d pixels exceeds the 2^31 slot index range", tile_w, tile_h);
+    ctx->slots_per_frame = (int)spf;
+    struct Arr { void** p; size_t elem; };
+    PathSoA& S = ctx->soa;
+    Queues& Q = ctx->queues;
+    std::vector<Arr> arrs = {
+        {(void**)&S.ray_o, 16}, {(void**)&S.ray_d, 16}, {(void**)&S.hit_f, 16}, {(void**)&S.hit_p, 16}, {(void**)&S.thr, 16}, {(void**)&S.rad, 16},
+        {(void**)&S.absn, 16}, {(void**)&S.stale, 16}, {(void**)&S.sf0, 16}, {(void**)&S.sf1, 16}, {(void**)&S.sf2, 16}, {(void**)&S.sf3, 16},
+        {(void**)&S.sf4, 16}, {(void**)&S.sh_o, 16}, {(void**)&S.sh_d0, 16}, {(void**)&S.sh_c0, 16}, {(void**)&S.sh_d1, 16}, {(void**)&S.sh_c1, 16},
+        {(void**)&S.sh_T, 16}, {(void**)&S.hit_i, 16}, {(void**)&S.rng, 16},
+        {(void**)&Q.active[0], 4}, {(void**)&Q.active[1], 4}, {(void**)&Q.shadow, 4}, {(void**)&Q.sample, 4},
+    };
+    if (ctx->sort_rays) { arrs.push_back({(void**)&ctx->sort.sorted, 4}); arrs.push_back({(void**)&ctx->sort.keys, 4}); }
+    size_t per_slot = 0;
+    for (const Arr& a : arrs) per_slot += a.elem;
+    int F = frames_req;
+    const bool autoF = F <= 0;
+    if (autoF) {
+        size_t slots = kAutoSlots;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) slots = std::min(slots, free_b / 2 / per_slot);
+        F = (int)std::min<size_t>(256, std::max<size_t>(1, slots / spf));
+    }
+    if ((size_t)F * spf > (size_t)INT_MAX)
+        return fail(ctx, LFCUDA_ELIMIT, "frames_in_flight %d x %zu slots per frame exceeds the 2^31 slot index range", F, spf);
+    for (;;) {
+        const size_t cap = (size_t)F * spf;
+        cudaError_t e = cudaSuccess;
+        for (const Arr& a : arrs) {
+            e = cudaMalloc(a.p, cap * a.elem);
+            if (e != cudaSuccess) { *a.p = nullptr; break; }
+            ctx->state_allocs.push_back(*a.p);
+        }
+        if (e == cudaSuccess && ctx->sort_rays) {
+            e = cudaMalloc((void**)&ctx->sort.hist, (size_t)kSortBins * sizeof(unsigned));
+            if (e == cudaSuccess) ctx->state_allocs.push_back(ctx->sort.hist);
+        }
+        if (e == cudaSuccess) { ctx->capacity = cap; break; }
+        free_state(ctx);
+        cudaGetLastError();   // clear the sticky allocation error
+        if (e != cudaErrorMemoryAllocation) return fail(ctx, LFCUDA_ECUDA, "path state allocation failed: %s", cudaGetErrorString(e));
+        if (!autoF || F == 1)
+            return fail(ctx, LFCUDA_ENOMEM, "path state of %d frames x %zu slots (%zu bytes per slot) does not fit the device", F, spf, per_slot);
+        F = std::max(1, F / 2);
+    }
+    ctx->frames_cap = F;
+    ctx->state_tile_w = tile_w; ctx->state_tile_h = tile_h; ctx->state_frames_req = frames_req;
     return 0;
 }
 
@@ -287,21 +355,31 @@ int run_batch(lfcuda_ctx* ctx, int first_frame, int nframes, int stride, int til
     return 0;
 }
 
-bool load_nccl(lfcuda_ctx* c) {
-    if (c->nccl.lib) return true;
+// The NCCL function table is bound once per process (dlopen is reference counted; the handle is kept for the process' life).
+Nccl g_nccl;
+std::mutex g_nccl_mutex;
+bool load_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (g_nccl.lib) return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-        c->nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-        if (c->nccl.lib) break;
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
     }
-    if (!c->nccl.lib) return false;
-    *(void**)&c->nccl.GetUniqueId = dlsym(c->nccl.lib, "ncclGetUniqueId");
-    *(void**)&c->nccl.CommInitRank = dlsym(c->nccl.lib, "ncclCommInitRank");
-    *(void**)&c->nccl.AllReduce = dlsym(c->nccl.lib, "ncclAllReduce");
-    *(void**)&c->nccl.CommDestroy = dlsym(c->nccl.lib, "ncclCommDestroy");
-    *(void**)&c->nccl.GetErrorString = dlsym(c->nccl.lib, "ncclGetErrorString");
-    return c->nccl.GetUniqueId && c->nccl.CommInitRank && c->nccl.AllReduce && c->nccl.CommDestroy;
+    if (!g_nccl.lib) return false;
+    *(void**)&g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+    *(void**)&g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+    *(void**)&g_nccl.CommInitAll = dlsym(g_nccl.lib, "ncclCommInitAll");
+    *(void**)&g_nccl.AllReduce = dlsym(g_nccl.lib, "ncclAllReduce");
+    *(void**)&g_nccl.GroupStart = dlsym(g_nccl.lib, "ncclGroupStart");
+    *(void**)&g_nccl.GroupEnd = dlsym(g_nccl.lib, "ncclGroupEnd");
+    *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.lib, "ncclCommDestroy");
+    *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
 }
+const char* nccl_err(int rc) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"; }
+// ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0; checked against the header of the NCCL this image ships)
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
 
 }  // namespace
 
@@ -342,10 +420,12 @@ void lfcuda_destroy(lfcuda_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     free_scene(c);
     free_state(c);
+    free_frame(c);
+    if (c->queues.counts) cudaFree(c->queues.counts);
     cudaFree(c->d_counters);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -368,8 +448,19 @@ int lfcuda_synchronize(lfcuda_ctx* ctx) {
     return 0;
 }
 
+static int upload_scene_impl(lfcuda_ctx* ctx, const LfSceneView* v);
 int lfcuda_upload_scene(lfcuda_ctx* ctx, const LfSceneView* v) {
     if (!ctx || !v) return LFCUDA_EINVAL;
+    int r = upload_scene_impl(ctx, v);
+    if (r) {   // the header promises that host arrays are copied during the call: no copy may still be in flight when we report
+        std::string err = ctx->err;
+        cudaStreamSynchronize(ctx->stream);
+        free_scene(ctx);
+        ctx->err = err;
+    }
+    return r;
+}
+static int upload_scene_impl(lfcuda_ctx* ctx, const LfSceneView* v) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     free_scene(ctx);
@@ -498,18 +589,22 @@ int lfcuda_update_instances(lfcuda_ctx* ctx, const float* transforms, int32_t nu
 
 int lfcuda_set_params(lfcuda_ctx* ctx, const LfParams* p) {
     if (!ctx || !p) return LFCUDA_EINVAL;
-    if (p->width <= 0 || p->height <= 0 || p->tile_width <= 0 || p->tile_height <= 0 || p->max_depth < 0)
-        return fail(ctx, LFCUDA_EINVAL, "bad resolution / tile size / depth");
+    if (p->width <= 0 || p->height <= 0 || p->tile_width <= 0 || p->tile_height <= 0 || p->max_depth < 0 || p->frames_in_flight < 0)
+        return fail(ctx, LFCUDA_EINVAL, "bad resolution / tile size / depth / frames_in_flight");
     CK(cudaSetDevice(ctx->device));
-    bool realloc = !ctx->have_params || p->width != ctx->params.width || p->height != ctx->params.height || p->tile_width != ctx->params.tile_width ||
-                   p->tile_height != ctx->params.tile_height || p->max_depth != ctx->params.max_depth || p->frames_in_flight != ctx->params.frames_in_flight;
+    // Only a change of the RESOLUTION re-creates (and thereby clears) the accumulation buffer - the reference re-creates its FBOs then
+    // too (Main.cpp reloads the renderer).  Tile size, depth, batch size and every other uniform leave the accumulated image alone.
+    const bool new_frame = !ctx->d_accum || p->width != ctx->frame_w || p->height != ctx->frame_h;
+    const bool new_state = !ctx->capacity || p->tile_width != ctx->state_tile_w || p->tile_height != ctx->state_tile_h ||
+                           p->frames_in_flight != ctx->state_frames_req;
+    if (new_frame || new_state) CK(cudaStreamSynchronize(ctx->stream));
+    int r = 0;
+    if (new_frame) r = alloc_frame(ctx, p->width, p->height);
+    if (!r && new_state) r = alloc_state(ctx, p->tile_width, p->tile_height, p->frames_in_flight);
+    if (!r) r = ensure_counts(ctx, p->max_depth);
+    if (r) { ctx->have_params = false; return r; }
     ctx->params = *p;
     ctx->have_params = true;
-    if (realloc) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        int r = alloc_state(ctx);
-        if (r) { ctx->have_params = false; return r; }
-    }
     return 0;
 }
 
@@ -556,19 +651,19 @@ int lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, 
     CK(cudaSetDevice(ctx->device));
     const size_t need = (size_t)pv_width * pv_height * 3;
     if (need > ctx->preview_cap) {
-        // grown on demand (previewScale changes reload the renderer in the reference, Main.cpp:525); freed with the path state
+        // grown on demand (previewScale changes reload the renderer in the reference, Main.cpp:525); freed with the frame buffers
         CK(cudaStreamSynchronize(ctx->stream));
         for (float* old : {ctx->d_preview, ctx->d_preview_out}) {   // a smaller pair from an earlier previewScale
             if (!old) continue;
             cudaFree(old);
-            ctx->state_allocs.erase(std::remove(ctx->state_allocs.begin(), ctx->state_allocs.end(), (void*)old), ctx->state_allocs.end());
+            ctx->frame_allocs.erase(std::remove(ctx->frame_allocs.begin(), ctx->frame_allocs.end(), (void*)old), ctx->frame_allocs.end());
         }
         ctx->d_preview = ctx->d_preview_out = nullptr; ctx->preview_cap = 0;
         float *a = nullptr, *b = nullptr;
         CK(cudaMalloc((void**)&a, need * sizeof(float)));
-        ctx->state_allocs.push_back(a);
+        ctx->frame_allocs.push_back(a);
         CK(cudaMalloc((void**)&b, need * sizeof(float)));
-        ctx->state_allocs.push_back(b);
+        ctx->frame_allocs.push_back(b);
         ctx->d_preview = a; ctx->d_preview_out = b; ctx->preview_cap = need;
     }
     ctx->preview_w = pv_width; ctx->preview_h = pv_height;
@@ -601,13 +696,15 @@ int lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, 
 
 // The preview target through the post-process pass, as Present()/SetViewport() show it (TiledRenderer.cpp:361-364,558-562;
 // invSampleCounter = 1 because Update() has reset sampleCounter to 1, :475).  pv_width * pv_height * 3 floats, rows bottom-up.
-int lfcuda_read_preview(lfcuda_ctx* ctx, int32_t tonemap_index, float* rgb_out) {
+int lfcuda_read_preview(lfcuda_ctx* ctx, int32_t tonemap_index, int32_t is_in_preview, float* rgb_out) {
     if (!ctx || !rgb_out) return fail(ctx, LFCUDA_EINVAL, "NULL context or output");
     if (!ctx->d_preview || ctx->preview_w < 1) return fail(ctx, LFCUDA_EINVAL, "no preview rendered (lfcuda_render_preview)");
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->preview_w * ctx->preview_h * 3;
     ctx->launches++;
-    launch_post(ctx->stream, ctx->d_preview, ctx->d_preview_out, nullptr, ctx->preview_w, ctx->preview_h, 1.0f, tonemap_index, ctx->post);
+    LfPostParams pp = ctx->post;
+    if (is_in_preview) pp.use_ca = 0;                       // postprocess.glsl:128-132: `if (!isInPreview) { ... useCA ... } else plain fetch`
+    launch_post(ctx->stream, ctx->d_preview, ctx->d_preview_out, nullptr, ctx->preview_w, ctx->preview_h, 1.0f, tonemap_index, pp);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, ctx->d_preview_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -656,49 +753,73 @@ int lfcuda_read_primary_hits(lfcuda_ctx* ctx, int32_t frame, float* t_out, int32
     if (r) return r;
     if (!t_out || !tri_out || !mat_out || !emitter_out) return fail(ctx, LFCUDA_EINVAL, "NULL output");
     CK(cudaSetDevice(ctx->device));
-    // The probe covers the full frame as one tile, like the llvmpipe probe shader run on a single-tile scene.
-    LfParams saved = ctx->params;
-    LfParams full = saved;
-    full.tile_width = saved.width; full.tile_height = saved.height; full.kernel_mode = 0;
-    if ((r = lfcuda_set_params(ctx, &full))) return r;
-    size_t n = (size_t)saved.width * saved.height;
-    float* d_t; int *d_tri, *d_mat, *d_em;
-    CK(cudaMalloc((void**)&d_t, n * 4)); CK(cudaMalloc((void**)&d_tri, n * 4)); CK(cudaMalloc((void**)&d_mat, n * 4)); CK(cudaMalloc((void**)&d_em, n * 4));
-    DevParams D;
-    fill_dev_params(ctx, D, frame, 1, 1, 0, 0);
-    LaunchCtx L;
-    make_launch_ctx(ctx, L, D);
-    CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)kCountRows * ctx->queues.stride * sizeof(int), ctx->stream));
-    { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
-    { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, 0); }
-    ctx->launches++;
-    launch_export_hits(L, d_t, d_tri, d_mat, d_em);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(t_out, d_t, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(tri_out, d_tri, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(mat_out, d_mat, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(emitter_out, d_em, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // The probe covers the full frame as one tile, like the llvmpipe probe shader run on a single-tile scene.  It never touches the
+    // accumulation buffer: it runs in the existing path state when one full frame fits it, and otherwise re-sizes the path state
+    // (only that group) for the duration of the call.  Parameters and state are restored on every exit path.
+    const LfParams saved = ctx->params;
+    const int saved_w8 = ctx->pix_w8, saved_h4 = ctx->pix_h4, saved_spf = ctx->slots_per_frame;
+    const int saved_tw = ctx->state_tile_w, saved_th = ctx->state_tile_h, saved_req = ctx->state_frames_req;
+    const size_t need = (size_t)((saved.width + 7) / 8 * 8) * ((saved.height + 3) / 4 * 4);
+    bool resized = false;
+    const size_t n = (size_t)saved.width * saved.height;
+    float* d_t = nullptr; int *d_tri = nullptr, *d_mat = nullptr, *d_em = nullptr;
+    auto body = [&]() -> int {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (need > ctx->capacity) {
+            resized = true;
+            int rr = alloc_state(ctx, saved.width, saved.height, 1);
+            if (rr) return rr;
+        } else {
+            ctx->pix_w8 = (saved.width + 7) / 8 * 8; ctx->pix_h4 = (saved.height + 3) / 4 * 4; ctx->slots_per_frame = (int)need;
+        }
+        ctx->params.tile_width = saved.width; ctx->params.tile_height = saved.height; ctx->params.kernel_mode = 0;
+        CK(cudaMalloc((void**)&d_t, n * 4)); CK(cudaMalloc((void**)&d_tri, n * 4)); CK(cudaMalloc((void**)&d_mat, n * 4)); CK(cudaMalloc((void**)&d_em, n * 4));
+        DevParams D;
+        fill_dev_params(ctx, D, frame, 1, 1, 0, 0);
+        LaunchCtx L;
+        make_launch_ctx(ctx, L, D);
+        CK(cudaMemsetAsync(ctx->queues.counts, 0, (size_t)kCountRows * ctx->queues.stride * sizeof(int), ctx->stream));
+        { StageTimer t(ctx, LF_STAGE_GENERATE); launch_generate(L); }
+        { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, 0); }
+        ctx->launches++;
+        launch_export_hits(L, d_t, d_tri, d_mat, d_em);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(t_out, d_t, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(tri_out, d_tri, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(mat_out, d_mat, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(emitter_out, d_em, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    r = body();
+    std::string err = ctx->err;
+    cudaStreamSynchronize(ctx->stream);
     cudaFree(d_t); cudaFree(d_tri); cudaFree(d_mat); cudaFree(d_em);
-    return lfcuda_set_params(ctx, &saved);
+    ctx->params = saved;
+    ctx->pix_w8 = saved_w8; ctx->pix_h4 = saved_h4; ctx->slots_per_frame = saved_spf;
+    if (resized) {
+        int r2 = alloc_state(ctx, saved_tw, saved_th, saved_req);
+        if (r2) { ctx->have_params = false; if (!r) return r2; }
+    }
+    if (r) ctx->err = err;
+    return r;
 }
 
 int lfcuda_nccl_unique_id(void* id128_out) {
     if (!id128_out) return LFCUDA_EINVAL;
-    lfcuda_ctx tmp;
-    if (!load_nccl(&tmp)) return fail(nullptr, LFCUDA_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
-    int rc = tmp.nccl.GetUniqueId(id128_out);
+    if (!load_nccl()) return fail(nullptr, LFCUDA_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    int rc = g_nccl.GetUniqueId(id128_out);
     return rc == 0 ? 0 : fail(nullptr, LFCUDA_ENCCL, "ncclGetUniqueId failed (%d)", rc);
 }
 
 int lfcuda_nccl_init(lfcuda_ctx* ctx, const void* id128, int32_t rank, int32_t nranks) {
     if (!ctx || !id128) return LFCUDA_EINVAL;
-    if (!load_nccl(ctx)) return fail(ctx, LFCUDA_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    if (!load_nccl()) return fail(ctx, LFCUDA_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
     CK(cudaSetDevice(ctx->device));
     NcclId id;
     std::memcpy(&id, id128, 128);
-    int rc = ctx->nccl.CommInitRank(&ctx->comm, nranks, id, rank);
-    if (rc != 0) return fail(ctx, LFCUDA_ENCCL, "ncclCommInitRank failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(rc) : "?");
+    int rc = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (rc != 0) return fail(ctx, LFCUDA_ENCCL, "ncclCommInitRank failed: %s", nccl_err(rc));
     return 0;
 }
 
@@ -706,9 +827,8 @@ int lfcuda_reduce(lfcuda_ctx* ctx) {
     if (!ctx || !ctx->have_params) return fail(ctx, LFCUDA_EINVAL, "render parameters not set");
     if (!ctx->comm) return fail(ctx, LFCUDA_ENCCL, "NCCL communicator not initialised (lfcuda_nccl_init)");
     CK(cudaSetDevice(ctx->device));
-    // ncclFloat32 = 7, ncclSum = 0
-    int rc = ctx->nccl.AllReduce(ctx->d_accum, ctx->d_accum, ctx->accum_floats, 7, 0, ctx->comm, ctx->stream);
-    if (rc != 0) return fail(ctx, LFCUDA_ENCCL, "ncclAllReduce failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(rc) : "?");
+    int rc = g_nccl.AllReduce(ctx->d_accum, ctx->d_accum, ctx->accum_floats, kNcclFloat32, kNcclSum, ctx->comm, ctx->stream);
+    if (rc != 0) return fail(ctx, LFCUDA_ENCCL, "ncclAllReduce failed: %s", nccl_err(rc));
     return 0;
 }
 
@@ -753,31 +873,37 @@ int lfcuda_measure_read_bandwidth(lfcuda_ctx* ctx, size_t bytes, int32_t iters, 
     CK(cudaSetDevice(ctx->device));
     size_t n4 = bytes / sizeof(float4);
     float4* buf = nullptr; float* sink = nullptr;
-    CK(cudaMalloc((void**)&buf, n4 * sizeof(float4)));
-    CK(cudaMalloc((void**)&sink, sizeof(float)));
-    CK(cudaMemsetAsync(buf, 0, n4 * sizeof(float4), ctx->stream));
-    int blocks = ctx->prop.multiProcessorCount * 8;
-    // enough passes per launch that the launch itself is negligible (>= ~256 MB read per launch)
-    int passes = (int)std::max<size_t>(1, ((size_t)256 << 20) / (n4 * sizeof(float4)));
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    launch_read_probe(ctx->stream, buf, n4, passes, sink, blocks);   // warm-up (fills L2 when the buffer fits)
+    cudaEvent_t a = nullptr, b = nullptr;
     double best = 0.0;
-    for (int it = 0; it < iters; it++) {
-        cudaEventRecord(a, ctx->stream);
-        launch_read_probe(ctx->stream, buf, n4, passes, sink, blocks);
-        cudaEventRecord(b, ctx->stream);
-        CK(cudaEventSynchronize(b));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, a, b);
-        double gbps = (double)n4 * sizeof(float4) * passes / (ms * 1e6);
-        if (gbps > best) best = gbps;
-        ctx->launches++;
-    }
-    cudaEventDestroy(a); cudaEventDestroy(b);
+    auto body = [&]() -> int {
+        CK(cudaMalloc((void**)&buf, n4 * sizeof(float4)));
+        CK(cudaMalloc((void**)&sink, sizeof(float)));
+        CK(cudaMemsetAsync(buf, 0, n4 * sizeof(float4), ctx->stream));
+        int blocks = ctx->prop.multiProcessorCount * 8;
+        // enough passes per launch that the launch itself is negligible (>= ~256 MB read per launch)
+        int passes = (int)std::max<size_t>(1, ((size_t)256 << 20) / (n4 * sizeof(float4)));
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        launch_read_probe(ctx->stream, buf, n4, passes, sink, blocks);   // warm-up (fills L2 when the buffer fits)
+        for (int it = 0; it < iters; it++) {
+            CK(cudaEventRecord(a, ctx->stream));
+            launch_read_probe(ctx->stream, buf, n4, passes, sink, blocks);
+            CK(cudaEventRecord(b, ctx->stream));
+            CK(cudaEventSynchronize(b));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            double gbps = (double)n4 * sizeof(float4) * passes / (ms * 1e6);
+            if (gbps > best) best = gbps;
+            ctx->launches++;
+        }
+        return 0;
+    };
+    int r = body();
+    cudaStreamSynchronize(ctx->stream);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
     cudaFree(buf); cudaFree(sink);
-    *gbps_out = best;
-    return 0;
+    if (!r) *gbps_out = best;
+    return r;
 }
 
 int lfcuda_get_launch_count(lfcuda_ctx* ctx, uint64_t* out) {

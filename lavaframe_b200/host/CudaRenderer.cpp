@@ -29,10 +29,21 @@ namespace LavaFrame
 
     CudaRenderer::~CudaRenderer()
     {
-        if (initialized) this->Finish();
+        this->Finish();                                      // frees the context whether or not Init completed
     }
 
     const char* CudaRenderer::LastError() const { return ctx ? lfcuda_last_error(ctx) : error.c_str(); }
+
+    // Init failed after the context was created: keep the message, release the device, leave the renderer not initialised
+    // (every entry point then returns at once, like the reference after a failed shader compile, Renderer.cpp:81-85).
+    void CudaRenderer::FailInit()
+    {
+        error = ctx ? lfcuda_last_error(ctx) : lfcuda_last_error(nullptr);
+        printf("CudaRenderer: %s\n", error.c_str());
+        if (ctx) lfcuda_destroy(ctx);
+        ctx = nullptr;
+        initialized = false;
+    }
 
     void CudaRenderer::Init()
     {
@@ -53,20 +64,16 @@ namespace LavaFrame
         previewDepth = scene->renderOptions.maxDepth;
         previewW = previewH = 0;
 
-        if (lfcuda_create(&ctx, device) != 0) {
-            error = lfcuda_last_error(nullptr);
-            printf("CudaRenderer: %s\n", error.c_str());    // like the reference: print and return (Renderer.cpp:81-85)
-            return;
-        }
+        if (lfcuda_create(&ctx, device) != 0) { ctx = nullptr; FailInit(); return; }
         LfSceneView view;
         lfhost::MakeSceneView(scene, &view);
-        if (lfcuda_upload_scene(ctx, &view) != 0) { printf("CudaRenderer: %s\n", lfcuda_last_error(ctx)); return; }
-        UploadUniforms();
-        if (lfcuda_clear(ctx) != 0) { printf("CudaRenderer: %s\n", lfcuda_last_error(ctx)); return; }
+        if (lfcuda_upload_scene(ctx, &view) != 0) { FailInit(); return; }       // e.g. a BVH deeper than the 64-entry stack
+        if (!UploadUniforms()) { FailInit(); return; }                           // e.g. path state does not fit the device
+        if (lfcuda_clear(ctx) != 0) { FailInit(); return; }
         initialized = true;
     }
 
-    void CudaRenderer::UploadUniforms()
+    bool CudaRenderer::UploadUniforms()
     {
         LfParams params;
         LfCamera cam;
@@ -77,17 +84,20 @@ namespace LavaFrame
         post.use_ca = ro.useCA ? 1 : 0; post.use_ca_distortion = ro.useCADistortion ? 1 : 0;
         post.ca_distance = ro.caDistance; post.ca_p1 = ro.caP1; post.ca_p2 = ro.caP2; post.ca_p3 = ro.caP3;
         post.use_vignette = ro.useVignette ? 1 : 0; post.vignette_intensity = ro.vignetteIntensity; post.vignette_power = ro.vignettePower;
-        if (lfcuda_set_params(ctx, &params) != 0 || lfcuda_set_camera(ctx, &cam) != 0 || lfcuda_set_post(ctx, &post) != 0)
+        if (lfcuda_set_params(ctx, &params) != 0 || lfcuda_set_camera(ctx, &cam) != 0 || lfcuda_set_post(ctx, &post) != 0) {
             printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+            return false;
+        }
+        return true;
     }
 
     void CudaRenderer::Finish()
     {
-        if (!initialized) return;
         pending.clear();
-        lfcuda_destroy(ctx);
+        if (ctx) lfcuda_destroy(ctx);
         ctx = nullptr;
-        Renderer::Finish();
+        if (initialized) Renderer::Finish();
+        initialized = false;
     }
 
     void CudaRenderer::Execute(size_t count)
@@ -179,7 +189,7 @@ namespace LavaFrame
         *data = nullptr;
         if (!initialized || previewW < 1) return;
         *data = new float[(size_t)w * h * 3];
-        if (lfcuda_read_preview(ctx, scene->renderOptions.tonemapIndex, *data) != 0)
+        if (lfcuda_read_preview(ctx, scene->renderOptions.tonemapIndex, scene->camera->isMoving ? 1 : 0, *data) != 0)
             printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
     }
 
@@ -187,7 +197,7 @@ namespace LavaFrame
     {
         w = scene->renderOptions.resolution.x;                       // TiledRenderer.cpp:399-414
         h = scene->renderOptions.resolution.y;
-        *data = new float[(size_t)w * h * 3];
+        *data = new float[(size_t)w * h * 3]();                     // zero-filled: a renderer that failed to initialise shows black
         if (!initialized) return;
         FlushCompletedSamples();
         int completed = sampleCounter - 1;                           // what tileOutputTexture[1 - currentBuffer] holds
@@ -200,7 +210,7 @@ namespace LavaFrame
     {
         w = scene->renderOptions.resolution.x;                       // TiledRenderer.cpp:382-397
         h = scene->renderOptions.resolution.y;
-        *data = new unsigned char[(size_t)w * h * 3];
+        *data = new unsigned char[(size_t)w * h * 3]();
         if (!initialized) return;
         FlushCompletedSamples();
         int completed = sampleCounter - 1;

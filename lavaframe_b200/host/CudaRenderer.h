@@ -41,6 +41,7 @@ namespace LavaFrame
 
         // Extras for drivers/tests (not part of the reference interface)
         lfcuda_ctx* Context() const { return ctx; }
+        bool Ok() const { return initialized && ctx != nullptr; }   // Init completed: scene uploaded, uniforms set, accumulation cleared
         const char* LastError() const;
         void Flush();                                            // execute every queued tile step now
         // The image Present()/SetViewport() display while the camera moves or before the first sample completes
@@ -52,7 +53,8 @@ namespace LavaFrame
         struct Step { int frame, tileX, tileY, sample; };
         void FlushCompletedSamples();
         void Execute(size_t count);
-        void UploadUniforms();
+        bool UploadUniforms();
+        void FailInit();
 
         lfcuda_ctx* ctx;
         int device;

@@ -77,7 +77,7 @@ void* lfhost_renderer_create(void* s, int device) {
     return r;
 }
 void lfhost_renderer_destroy(void* r) { delete static_cast<CudaRenderer*>(r); }
-int  lfhost_renderer_ok(void* r) { return static_cast<CudaRenderer*>(r)->Context() != nullptr; }
+int  lfhost_renderer_ok(void* r) { return static_cast<CudaRenderer*>(r)->Ok() ? 1 : 0; }
 const char* lfhost_renderer_error(void* r) { return static_cast<CudaRenderer*>(r)->LastError(); }
 void lfhost_renderer_update(void* r, float dt) { static_cast<Renderer*>(static_cast<CudaRenderer*>(r))->Update(dt); }
 void lfhost_renderer_render(void* r) { static_cast<Renderer*>(static_cast<CudaRenderer*>(r))->Render(); }
@@ -113,6 +113,7 @@ void lfhost_set_preview(float scale, int use_dof) { GlobalState.previewScale = s
 // Main.cpp's loop (MainLoop :313-755 -> Update :160-234 -> Render :99-158) for `spp` samples: the auto-stop test
 // `maxSamples + 1 == GetSampleCount()` comes first, then renderer->Update, then renderer->Render.
 int lfhost_renderer_run(void* rv, int spp) {
+    if (!static_cast<CudaRenderer*>(rv)->Ok()) return -1;   // a renderer whose Init failed never advances its sample counter
     Renderer* r = static_cast<Renderer*>(static_cast<CudaRenderer*>(rv));
     int steps = 0;
     while (true) {

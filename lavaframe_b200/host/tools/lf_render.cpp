@@ -52,7 +52,7 @@ int main(int argc, char** argv) {
     CudaRenderer* r = new CudaRenderer(GlobalState.scene, GlobalState.shadersDir, device);   // Main.cpp:91
     GlobalState.renderer = r;
     r->Init();
-    if (!r->Context()) { fprintf(stderr, "lf_render: %s\n", r->LastError()); return 3; }
+    if (!r->Ok()) { fprintf(stderr, "lf_render: %s\n", r->LastError()); return 3; }
     auto t0 = std::chrono::steady_clock::now();
     int steps = 0;
     while (true) {

@@ -89,11 +89,11 @@ class PathTracer:
     def render_frames(self, first_frame, nframes, frame_stride=1, tile_x=0, tile_y=0):
         self._ck(self.lib.lfcuda_render_frames(self.h, first_frame, nframes, frame_stride, tile_x, tile_y), "lfcuda_render_frames")
 
-    def render_preview(self, pv_width, pv_height, max_depth=2, use_dof=False, tonemap_index=0):
+    def render_preview(self, pv_width, pv_height, max_depth=2, use_dof=False, tonemap_index=0, is_in_preview=False):
         """The preview engine (preview_flareon.glsl): renders and returns the pv_height x pv_width x 3 image, rows bottom-up."""
         self._ck(self.lib.lfcuda_render_preview(self.h, pv_width, pv_height, max_depth, int(use_dof)), "lfcuda_render_preview")
         out = np.empty((pv_height, pv_width, 3), np.float32)
-        self._ck(self.lib.lfcuda_read_preview(self.h, tonemap_index, out.ctypes.data_as(C.c_void_p)), "lfcuda_read_preview")
+        self._ck(self.lib.lfcuda_read_preview(self.h, tonemap_index, 1 if is_in_preview else 0, out.ctypes.data_as(C.c_void_p)), "lfcuda_read_preview")
         return out
 
     def synchronize(self):

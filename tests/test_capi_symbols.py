@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = lf.load_lfcuda()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.lfcuda_abi_version() == 1
+    assert lib.lfcuda_abi_version() == 2
 
 
 def test_struct_sizes_match_the_header():

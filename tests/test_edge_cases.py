@@ -134,6 +134,44 @@ def test_deep_chain_bvh_uses_the_64_entry_stack(tracer, tmp_path, oracle_lib):
     o.close()
 
 
+def test_distant_light_branch(tracer, tmp_path, oracle_lib):
+    """sampleDistantLight (sampling.glsl:208-216, light type 2): the loader never writes one, the shader and both restatements
+    carry the branch.  A hand-built pack with a distant light next to a quad light: CUDA == oracle on every bit."""
+    zc = 12 + 6.0
+    lights = [synth_pack.distant_light((0.3, 0.5, 1.0), (2.0, 1.5, 1.0)),
+              synth_pack.quad_light((-1.0, -1.0, zc), (0.0, 3.0, 0.0), (6.0, 0.0, 0.0), (20.0, 20.0, 20.0))]
+    path = synth_pack.chain_scene(str(tmp_path / "distant.lfpack"), 12, lights=lights)
+    pack = lf.ScenePack(path)
+    o = Oracle(path)
+    ref = o.render_frames(2, 8)
+    only_quad = Oracle(synth_pack.chain_scene(str(tmp_path / "quad.lfpack"), 12)).render_frames(2, 8)
+    assert not np.array_equal(ref, only_quad)                    # the distant light does light the scene
+    for mode in (0, 1):
+        tracer.upload_pack(pack, kernel_mode=mode)
+        tracer.clear(); tracer.render_frames(2, 8)
+        assert_same(tracer.read_accum(), ref, f"distant light, mode {mode}")
+    o.close()
+
+
+def test_axis_ray_on_flat_box_plane(tracer, tmp_path, oracle_lib):
+    """KAT for AABBIntersect's NaN semantics (synth_pack.axis_ray_scene): d.z == 0 exactly, origin on the
+    plane of a z-flat box.  llvmpipe's MINPS / MAXPS make t1 NaN and the box a miss; the GPU's FMNMX would make it a hit."""
+    path = synth_pack.axis_ray_scene(str(tmp_path / "axis.lfpack"))
+    pack = lf.ScenePack(path)
+    o = Oracle(path)
+    ohits = o.primary_hits(2)
+    assert (ohits[1] == 3).all() and (ohits[0] > 9.9).all()      # the reference walks past the flat box to the far triangle
+    for no_cull in (0, 1):
+        tracer.upload_pack(pack, no_cull=no_cull)
+        for a, b in zip(tracer.primary_hits(2), ohits):
+            assert np.array_equal(a, b)
+        for mode in (0, 1):
+            tracer.update_params(kernel_mode=mode)
+            tracer.clear(); tracer.render_frames(2, 2)
+            assert_same(tracer.read_accum(), o.render_frames(2, 2), f"axis ray, no_cull {no_cull}, mode {mode}")
+    o.close()
+
+
 def test_bvh_deeper_than_the_reference_stack_is_refused(tracer, tmp_path):
     pack = lf.ScenePack(synth_pack.chain_scene(str(tmp_path / "chain70.lfpack"), 70))
     with pytest.raises(lf.LfCudaError, match="deeper than 64"):
@@ -150,6 +188,42 @@ def test_empty_work(tracer, golden_dir):
     img, ref = both(tracer, pack, cam=dict(forward=(C.c_float * 3)(0.0, 0.0, -1.0)))
     assert not ref.any()
     assert_same(img, ref, "camera looking away")
+
+
+def test_uniform_changes_keep_the_accumulation(tracer, golden_dir, oracle_lib):
+    """The reference changes maxDepth / tile uniforms without touching accumTexture (TiledRenderer.cpp:505-521).  Here: the
+    primary-hit probe with tile != resolution, a new max_depth and a new batch size all leave the accumulated image and its
+    device address (lfcuda_accum_device_ptr, what NCCL reduces) alone; only a new resolution re-creates the buffer."""
+    pack = lf.ScenePack(os.path.join(golden_dir, "cornell.lfpack"))
+    tracer.upload_pack(pack, tile_width=64, tile_height=64)
+    tracer.clear(); tracer.render_frames(2, 2, 1, 1, 2)
+    img0 = tracer.read_accum()
+    ptr0 = tracer.accum_device_ptr()
+    assert img0.any()
+    hits = tracer.primary_hits(2)
+    assert np.array_equal(tracer.read_accum(), img0) and tracer.accum_device_ptr() == ptr0
+    tracer.update_params(max_depth=2)
+    assert np.array_equal(tracer.read_accum(), img0) and tracer.accum_device_ptr() == ptr0
+    tracer.update_params(max_depth=6, frames_in_flight=3)
+    assert np.array_equal(tracer.read_accum(), img0) and tracer.accum_device_ptr() == ptr0
+    tracer.update_params(tile_width=128, tile_height=32, frames_in_flight=0)
+    assert np.array_equal(tracer.read_accum(), img0) and tracer.accum_device_ptr() == ptr0
+    # ... and the probe's answer does not depend on the tile size it was called under
+    tracer.update_params(tile_width=pack.width, tile_height=pack.height)
+    for a, b in zip(hits, tracer.primary_hits(2)):
+        assert np.array_equal(a, b)
+    # the state still renders correctly after all of that: tile (0, 0) of 128 x 32 at depth 6 on top of the old image
+    tracer.update_params(tile_width=128, tile_height=32)
+    tracer.render_frames(5, 1, 1, 0, 0)
+    o = Oracle(pack.path)
+    o.update_params(tile_width=64, tile_height=64)
+    ref = o.render_frames(2, 2, 1, 1, 2)
+    o.update_params(tile_width=128, tile_height=32, max_depth=6)
+    ref = o.render_frames(5, 1, 1, 0, 0, accum=ref)
+    o.close()
+    assert_same(tracer.read_accum(), ref, "accumulation across uniform changes")
+    tracer.update_params(width=128, height=128, tile_width=128, tile_height=128)      # a new resolution starts from black
+    assert not tracer.read_accum().any()
 
 
 def test_bad_arguments_are_reported(gpu, golden_dir):

@@ -165,3 +165,38 @@ def test_device_source_bsdf_vs_llvmpipe(golden_dir, hostcheck, op):
     hostcheck.lfhc_bsdf_kat(op, a.ctypes.data, a.shape[0], out.ctypes.data)
     same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref)) | ((out == 0) & (ref == 0))
     assert same.all(), f"{BSDF_OPS[op]}: {int((~same.all(axis=1)).sum())} of {same.shape[0]} items differ from llvmpipe"
+
+
+def test_axis_ray_on_flat_box_plane(tmp_path, oracle_lib, hostcheck):
+    """NaN semantics of AABBIntersect (intersection.glsl:53-67 with llvmpipe's MINPS / MAXPS): a ray with d.z == 0 whose origin
+    lies on the plane of a z-flat box misses that box in the reference (0 * inf = NaN slabs); the device source must too."""
+    import synth_pack
+    path = synth_pack.axis_ray_scene(str(tmp_path / "axis.lfpack"))
+    o = Oracle(path)
+    t, tri, _, _ = o.primary_hits(2)
+    ref = o.render_frames(2, 2)
+    o.close()
+    assert (tri == 3).all() and (t > 9.9).all()          # the far triangle: the flat box in front of it was missed
+    h = hostcheck.lfhc_open_pack(path.encode())
+    assert h
+    for cull in (0, 1):
+        img = np.zeros_like(ref)
+        assert hostcheck.lfhc_render_frames(h, 2, 2, 1, cull, img.ctypes.data) == 0
+        assert np.array_equal(img, ref)
+    hostcheck.lfhc_close(h)
+
+
+def test_distant_light_branch(tmp_path, oracle_lib, hostcheck):
+    """sampleDistantLight (sampling.glsl:208-216; light type 2, never written by the loader): device source == oracle."""
+    import synth_pack
+    lights = [synth_pack.distant_light((0.3, 0.5, 1.0), (2.0, 1.5, 1.0)),
+              synth_pack.quad_light((-1.0, -1.0, 18.0), (0.0, 3.0, 0.0), (6.0, 0.0, 0.0), (20.0, 20.0, 20.0))]
+    path = synth_pack.chain_scene(str(tmp_path / "distant.lfpack"), 12, lights=lights)
+    o = Oracle(path)
+    ref = o.render_frames(2, 8)
+    o.close()
+    h = hostcheck.lfhc_open_pack(path.encode())
+    img = np.zeros_like(ref)
+    assert hostcheck.lfhc_render_frames(h, 2, 8, 1, 1, img.ctypes.data) == 0
+    hostcheck.lfhc_close(h)
+    assert ref.any() and np.array_equal(img, ref)

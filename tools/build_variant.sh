@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 defs=""; for a in "$@"; do case $a in -D*) defs="$defs $a";; esac; done   # only the -D flags go to g++
 mkdir -p ab build/ab
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -std=c++17 \
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=${LF_FMAD:-false} -Xcompiler -fPIC -std=c++17 \
      -Iinclude -Ilavaframe_b200/csrc "$@" -c lavaframe_b200/csrc/lf_kernels.cu -o build/ab/$name.kernels.o
 g++ -O2 -fPIC -std=c++17 -ffp-contract=off -Iinclude -Ilavaframe_b200/csrc -I/usr/local/cuda/include $defs -c lavaframe_b200/csrc/lfcuda.cpp -o build/ab/$name.lfcuda.o
 g++ -O2 -fPIC -std=c++17 -ffp-contract=off -Iinclude -Ilavaframe_b200/csrc -I/usr/local/cuda/include $defs -c lavaframe_b200/csrc/lf_repack.cpp -o build/ab/$name.repack.o
