@@ -101,64 +101,91 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU side
-def oracle_sample_rate(pack_path, budget_s, tile=(320, 180)):
-    """Oracle port on a bounded sample: the centre tile of the frame, as many spp as fit the time budget."""
-    from oracle_api import Oracle
-    o = Oracle(pack_path)
-    W, H = o.params.width, o.params.height
+def stratified_tiles(W, H, tile=(80, 45), grid=4):
+    """A stratified sample of the frame for the CPU arms: the frame is cut into tiles of `tile` pixels (shrunk to divide the frame)
+    and grid x grid of them are taken, one from the middle of every cell of a grid x grid partition of the tile lattice - sky, horizon,
+    mesh and ground are all represented in proportion, unlike a single centre tile (which is the most expensive part of the frame)."""
     tw, th = min(tile[0], W), min(tile[1], H)
     while W % tw:
         tw -= 1
     while H % th:
         th -= 1
-    o.update_params(tile_width=tw, tile_height=th)
-    tx, ty = (W // tw) // 2, (H // th) // 2
-    t0 = time.time()
-    o.render_frames(2, 1, 1, tx, ty)
-    t1 = time.time() - t0
+    ntx, nty = W // tw, H // th
+    gx, gy = min(grid, ntx), min(grid, nty)
+    tiles = sorted({(int((i + 0.5) * ntx / gx), int((j + 0.5) * nty / gy)) for i in range(gx) for j in range(gy)})
+    return tw, th, tiles
+
+
+class OracleSampler:
+    """The oracle port on a bounded, stratified sample of the workload: `spp` frames of every sampled tile per call."""
+
+    def __init__(self, pack_path):
+        import oracle_api
+        from oracle_api import Oracle
+        # torchrun exports OMP_NUM_THREADS=1 to its ranks: ask for every host core explicitly and report what OpenMP really uses
+        self.threads = oracle_api.set_threads(os.cpu_count() or 1)
+        self.o = Oracle(pack_path)
+        self.W, self.H = self.o.params.width, self.o.params.height
+        self.tw, self.th, self.tiles = stratified_tiles(self.W, self.H)
+        self.o.update_params(tile_width=self.tw, tile_height=self.th)
+        self.frame = 2
+
+    def render(self, spp):
+        t0 = time.time()
+        for tx, ty in self.tiles:
+            self.o.render_frames(self.frame, spp, 1, tx, ty)
+        self.frame += spp
+        return time.time() - t0
+
+    def samples(self, spp):
+        return self.tw * self.th * len(self.tiles) * spp
+
+    def describe(self, spp):
+        frac = self.tw * self.th * len(self.tiles) / (self.W * self.H)
+        return (f"oracle port (CPU restatement of the GLSL, OpenMP, {self.threads} threads): {len(self.tiles)} tiles of {self.tw}x{self.th} stratified "
+                f"over the {self.W}x{self.H} frame ({frac:.3f} of its pixels), {spp} spp per step")
+
+    def close(self):
+        self.o.close()
+
+
+def oracle_sample_rate(pack_path, budget_s):
+    """cpu_baseline of the CUDA arm: the oracle port on the stratified sample, as many spp as fit the time budget."""
+    sm = OracleSampler(pack_path)
+    sm.render(1)                                       # first touch of the scene arrays
+    t1 = sm.render(1)
     spp = int(max(2, min(512, budget_s / max(t1, 1e-3))))
-    t0 = time.time()
-    o.render_frames(3, spp, 1, tx, ty)
-    dt = time.time() - t0
-    o.close()
-    return tw * th * spp / dt, f"centre tile {tw}x{th} of the {W}x{H} frame, {spp} spp, frames 3..{spp + 2} ({tw * th * spp} pixel-samples, {dt:.1f} s)"
+    dt = sm.render(spp)
+    sample = sm.describe(spp) + f" ({sm.samples(spp)} pixel-samples, {dt:.1f} s)"
+    threads = sm.threads
+    sm.close()
+    return sm.samples(spp) / dt, sample, threads
 
 
 def run_reference(args, workload, desc):
-    """--impl reference: the reference's own CPU path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU path on the host cores (rank 0 only; the other ranks exit without work)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     pack = ensure_pack(WORKLOADS[workload][0])
-    cores = os.cpu_count()
-    from oracle_api import Oracle
-    o = Oracle(pack)
-    W, H = o.params.width, o.params.height
-    tw, th = 320, 180
-    while W % tw:
-        tw -= 1
-    while H % th:
-        th -= 1
-    o.update_params(tile_width=tw, tile_height=th)
-    tx, ty = (W // tw) // 2, (H // th) // 2
-    t0 = time.time(); o.render_frames(2, 1, 1, tx, ty); t1 = time.time() - t0
+    sm = OracleSampler(pack)
+    sm.render(1)                                       # first touch of the scene arrays
+    t1 = sm.render(1)
     # size one step so that warmup + steps finish within ~2.5 minutes
     per_step_budget = min(2.0, 150.0 / max(1, args.steps + args.warmup))
     spp = int(max(1, min(256, per_step_budget / max(t1, 1e-3))))
-    frame = 3
     for _ in range(args.warmup):
-        o.render_frames(frame, spp, 1, tx, ty); frame += spp
-    t0 = time.time()
-    for _ in range(args.steps):
-        o.render_frames(frame, spp, 1, tx, ty); frame += spp
-    dt = time.time() - t0
-    o.close()
-    value = tw * th * spp * args.steps / dt
-    sample = f"oracle port (CPU restatement of the GLSL, OpenMP): centre tile {tw}x{th} of the {W}x{H} frame, {spp} spp per step"
+        sm.render(spp)
+    dt = sum(sm.render(spp) for _ in range(args.steps))
+    value = sm.samples(spp) * args.steps / dt
+    sample = sm.describe(spp)
+    W, H, threads = sm.W, sm.H, sm.threads
+    sm.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "spp_per_step": spp, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": desc, "resolution": [W, H], "spp_per_step": spp, "sample": sample, "same_config": True,
+                   "same_config_note": "same scene, resolution, depth and RNG frames as the CUDA arm; a stratified subset of its pixels (every host thread busy), rate in samples/s"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,7 +197,7 @@ def run_reference(args, workload, desc):
             v = lp["samples_per_s_steady"]
             what = f"the unmodified reference renderer + GLSL on Mesa llvmpipe ({lp['gl']}), steady state after the shader JIT: {lp['workload']}"
             line["value"] = v
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "reference", "sample": what}
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": lp["threads"], "host_cores": os.cpu_count(), "kind": "reference", "sample": what}
             line["e2e"]["value"] = v
             line["config"]["sample"] = what
             line["llvmpipe"] = lp
@@ -204,8 +231,10 @@ def llvmpipe_rate(workload):
         res = subprocess.run([ref, "--scene", scene, "--spp", str(spp), "--out", f"/tmp/lf_{workload}_llvmpipe.f32", "--timing-json"],
                              env=gen_scenes.llvmpipe_env(), capture_output=True, text=True, timeout=900, check=True)
         j = json.loads(res.stdout.strip().splitlines()[-1])
+        lpt = str(j["lp_num_threads"])
+        threads = int(lpt) if lpt.isdigit() else min(os.cpu_count() or 1, 16)     # Mesa 18.1 llvmpipe: one rasteriser thread per core, at most LP_MAX_THREADS = 16
         return {"kind": "reference", "workload": what, "samples_per_s_steady": j["samples_per_s_steady"], "first_step_s": j["first_step_s"],
-                "render_s": j["render_s"], "cores": os.cpu_count(), "lp_num_threads": j["lp_num_threads"], "gl": j["gl_renderer"] + " / " + j["gl_version"]}
+                "render_s": j["render_s"], "cores": os.cpu_count(), "threads": threads, "lp_num_threads": j["lp_num_threads"], "gl": j["gl_renderer"] + " / " + j["gl_version"]}
     except Exception as e:  # the reference arm must not take the bench down
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
@@ -234,6 +263,8 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=0, help="pixel-sample frames per wavefront batch (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-llvmpipe", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the c5_strong record (4K scene, 4096 spp in total, strong scaling)")
+    ap.add_argument("--c5-spp", type=int, default=4096)
     args = ap.parse_args()
     gen_name, desc, full_spp = WORKLOADS[args.workload]
 
@@ -290,6 +321,13 @@ def main():
     def sync():
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- warm-up
     for i in range(Wm):
         f0, st = step_frames(i)
@@ -321,16 +359,20 @@ def main():
     launches = pt.launch_count() - launches0
     stats1 = pt.stage_stats()
     pt.set_profiling(False)
+    ms = max_over_ranks(ms)
     if world > 1:
-        tms = torch.tensor([ms], device="cuda"); dist.all_reduce(tms, op=dist.ReduceOp.MAX); ms = float(tms.item())
         tl = torch.tensor([launches], device="cuda", dtype=torch.int64); dist.all_reduce(tl); launches = int(tl.item())
     total_samples = npix * S * K * world
     value = total_samples / (ms * 1e-3)
 
-    # ---- e2e through the C ABI with host buffers: uniforms in, accumulated image out, every step
+    # ---- e2e through the C ABI with host buffers: uniforms in every step; the finished image out.  Every step uploads its uniforms
+    # (host structs), renders, and reads the accumulated image back to host memory; at N > 1 the read-out of a step is the NCCL sum
+    # (lfcuda_reduce, in place) of the ranks' buffers, so each rank's accumulator is cleared per step and the host adds the steps up -
+    # the progressive image a viewer of the multi-GPU job would be shown after every step.
     host_img = torch.empty((H, W, 3), dtype=torch.float32).pin_memory().numpy()
+    host_sum = np.zeros((H, W, 3), np.float32) if world > 1 else None
     h2d = ctypes.sizeof(lf.LfParams) + ctypes.sizeof(lf.LfCamera)
-    d2h = npix * 3 * 4 if rank == 0 else 0
+    d2h = npix * 3 * 4
     pt.clear()
     barrier(); sync()
     t0 = time.perf_counter()
@@ -338,22 +380,40 @@ def main():
     for i in range(K):
         f0, st = step_frames(Wm + K + i)
         pt.set_params(pt.params); pt.set_camera(pack.camera())       # host structs -> device uniforms
+        if world > 1:
+            pt.clear()
         pt.render_frames(f0, S, st)
         if world > 1:
-            # out-of-place sum for read-out: reduce a snapshot so that the local accumulator keeps only local samples
-            ptr, n = pt.accum_device_ptr()
-            snap = torch.as_tensor(_DevBuf(ptr, n), device="cuda").clone()
-            dist.all_reduce(snap)
-            if rank == 0:
-                torch.from_numpy(host_img.reshape(-1)).copy_(snap, non_blocking=False)
-        else:
-            pt.read_accum(host_img)                                   # D2H + synchronize
+            pt.reduce()                                               # lfcuda_reduce: ncclAllReduce of the accumulation buffers
+        pt.read_accum(host_img)                                       # D2H + synchronize (every rank holds the sum)
+        if world > 1 and rank == 0:
+            host_sum += host_img
     e1.record(stream)
     sync(); barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    if world > 1:
-        tms = torch.tensor([e2e_ms], device="cuda"); dist.all_reduce(tms, op=dist.ReduceOp.MAX); e2e_ms = float(tms.item())
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
     e2e_value = total_samples / (e2e_ms * 1e-3)
+
+    # ---- N > 1: proof that the NCCL sum is the image.  A bounded job (the first `cf` frames) is rendered split over the ranks and summed
+    # by lfcuda_reduce, then rendered whole by rank 0 alone; the two must agree up to fp32 summation order.
+    reduce_check = None
+    if world > 1:
+        cf = 8 * world
+        f0, n, st = rank_frames(2, cf, rank, world)
+        pt.clear(); pt.render_frames(f0, n, st); pt.reduce()
+        reduced = pt.read_accum().copy()
+        same_everywhere = torch.tensor([float(np.float64(reduced.sum(dtype=np.float64)))], device="cuda", dtype=torch.float64)
+        lo, hi = same_everywhere.clone(), same_everywhere.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            pt.clear(); pt.render_frames(2, cf, 1)
+            single = pt.read_accum()
+            err = np.abs(reduced - single)
+            tol = 2e-5 * np.abs(single) + 1e-5
+            reduce_check = {"frames": cf, "ranks": world, "max_abs_err": float(err.max()), "max_rel_err": float((err / np.maximum(np.abs(single), 1e-3)).max()),
+                            "allclose_rtol_2e-5": bool((err <= tol).all()), "all_ranks_hold_the_same_sum": bool(lo.item() == hi.item()),
+                            "what": "lfcuda_reduce(sum of the ranks' strided frames) vs rank 0 rendering the same frames alone"}
+            assert reduce_check["allclose_rtol_2e-5"] and reduce_check["all_ranks_hold_the_same_sum"], f"NCCL-reduced image != single-GPU image: {reduce_check}"
+        barrier()
 
     # ---- roofline of the dominant kernel (extend): visit counts from an instrumented pass over the first timed steps
     ncount = min(K, 2)
@@ -373,9 +433,9 @@ def main():
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
+        hbm_peak, hbm_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
     else:
-        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+        hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
     traffic = None
     prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
     if os.path.exists(prof):
@@ -384,32 +444,32 @@ def main():
         except Exception:
             traffic = None
     rays = c["rays_closest"] + c["rays_shadow"]
+    # The walk is served by L1 / L2, not HBM (DRAM traffic = `traffic`, a few per cent of the algorithmic bytes), so the roofline that
+    # bounds it is the L2 -> SM read rate, measured in this run (16 MiB working set, the 16-byte read-only loads the traversal uses).
+    # `frac_of_hbm` (against MEASURED_PEAKS.json) stays beside it, and so does the ceiling of the bound ncu names (L1 data-pipe
+    # wavefronts: one-node-per-lane 2 x 256-bit fetches that hit L2), also measured in this run.
+    l2 = hbm_read = node_l2 = node_l1 = None
+    try:
+        l2 = pt.measure_read_bandwidth(16 << 20, 10)
+        hbm_read = pt.measure_read_bandwidth(2 << 30, 3)
+        node_l2 = pt.measure_node_fetch(8 << 20, 5)
+        node_l1 = pt.measure_node_fetch(32 << 10, 5)
+    except Exception as e:
+        log(f"[bench] bandwidth probes failed: {e}")
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "launches": dom_launches, "ms_per_launch": dom_ms / dom_launches, "bytes_per_launch": dom_bytes / dom_launches,
+        "bound": "l2", "kernel": dom, "achieved": achieved, "peak": l2, "unit": "GB/s", "frac": achieved / l2 if l2 else None, "traffic": traffic,
+        "peak_source": "L2 -> SM read rate measured in this run (lfcuda_measure_read_bandwidth, 16 MiB working set)",
+        "frac_of_l2": achieved / l2 if l2 else None,
+        "hbm_peak": hbm_peak, "hbm_peak_source": hbm_src, "frac_of_hbm": achieved / hbm_peak,
+        "l2_read_gbs_measured": l2, "hbm_read_gbs_measured": hbm_read,
+        "l1_node_fetch_ceiling_gbs": node_l2, "l1_node_fetch_l1hit_gbs": node_l1,
+        "frac_of_l1_node_fetch_ceiling": achieved / node_l2 if node_l2 else None,
+        "l1_node_fetch_source": "lfcuda_measure_node_fetch in this run: 64-byte records, one per lane, 2 x LDG.256, 8 MiB table (L2 hits) / 32 KiB table (L1 hits)",
+        "launches": dom_launches, "ms_per_launch": dom_ms / dom_launches, "bytes_per_launch": dom_bytes / dom_launches,
         "bytes_per_ray": (ext_bytes + sh_bytes) / max(1, rays),
         "stage_ms": {k: round(v["ms"], 3) for k, v in stage.items()},
         "shadow_achieved_gbs": sh_bytes * scale / (stage["shadow"]["ms"] * 1e-3) / 1e9 if stage["shadow"]["ms"] > 0 else None,
     }
-    if rank == 0:   # the L2 denominator north_star asks for (not in MEASURED_PEAKS.json): measured here, 16 MiB working set
-        try:
-            l2 = pt.measure_read_bandwidth(16 << 20, 10)
-            hbm_read = pt.measure_read_bandwidth(2 << 30, 3)
-            roofline["l2_read_gbs_measured"] = l2
-            roofline["hbm_read_gbs_measured"] = hbm_read
-            roofline["frac_of_l2"] = achieved / l2
-        except Exception as e:
-            roofline["l2_read_gbs_measured"] = f"failed: {e}"
-    # the bound that ncu shows to be the active one (l1tex data-pipe wavefronts): the rate at which this GPU delivers
-    # divergent 64-byte node fetches that hit L2, measured by tools/l1_probe.cu and recorded under profiles/
-    ceil_path = os.path.join(ROOT, "profiles", "l1_fetch_ceiling.json")
-    if os.path.exists(ceil_path):
-        try:
-            ceil = json.load(open(ceil_path))["node_fetch_l2_hit_gbs"]
-            roofline["l1_node_fetch_ceiling_gbs"] = ceil
-            roofline["frac_of_l1_node_fetch_ceiling"] = achieved / ceil
-        except Exception:
-            pass
     mrays = rays * scale * world / (ms * 1e-3) / 1e6
 
     line = {
@@ -418,23 +478,88 @@ def main():
         "config": {"workload": desc, "resolution": [W, H], "spp_per_step": S, "spp_total": S * K * world, "full_config_spp": full_spp,
                    "max_depth": pt.params.max_depth, "parallelism": f"spp-split x{world}" if world > 1 else "single GPU",
                    "kernels": "megakernel" if args.kernel_mode == 1 else "wavefront",
-                   "l2_policy": "scene geometry (~165 MB) + 4 M-path state (~1 GB) exceed the 126 MB L2 every step; no flush needed"},
+                   "l2_policy": "scene geometry (~165 MB) + 32 M-path state (~11 GB) exceed the 126 MB L2 every step; no flush needed"},
         "mrays_per_s": mrays, "rays_per_sample": rays / max(1, c["samples"]),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
-                "path": "lfcuda_set_params + lfcuda_set_camera + lfcuda_render_frames + lfcuda_read_accum (host buffers)"},
+                "path": ("lfcuda_set_params + lfcuda_set_camera + lfcuda_render_frames + lfcuda_read_accum (host buffers)" if world == 1 else
+                         "lfcuda_set_params + lfcuda_set_camera + lfcuda_clear + lfcuda_render_frames + lfcuda_reduce (NCCL) + lfcuda_read_accum (host buffers), every step, every rank")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    if reduce_check is not None:
+        line["reduce_check"] = reduce_check
+    pt.close()
+
+    # ---- north_star's scaling config (C5): the 4K scene at 4096 spp in total, split over the ranks (STRONG scaling), NCCL sum inside
+    if not args.no_c5 and args.workload == "c2_full" and args.kernel_mode == 0:
+        try:
+            line["c5_strong"] = c5_strong(args, rank, local_rank, world, stream, barrier, max_over_ranks)
+        except Exception as e:   # the headline line must survive
+            line["c5_strong"] = {"failed": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, sample = oracle_sample_rate(pack_path, 12.0)
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+            v, sample, threads = oracle_sample_rate(pack_path, 12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": sample}
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    pt.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def c5_strong(args, rank, local_rank, world, stream, barrier, max_over_ranks):
+    """BASELINE.json configs[4]: the 4K synthetic scene (C4) at 4096 spp IN TOTAL, the frames dealt round-robin to the ranks (4096 / N
+    per rank), accumulation buffers summed by lfcuda_reduce (NCCL) inside the timed region.  Total work is fixed as N grows: the
+    driver's N = 1, 2, 4, 8 runs of this record are north_star's strong-scaling figure (>= 7x at 8 GPUs)."""
+    import torch
+    import torch.distributed as dist
+    import lavaframe_b200 as lf
+    from lavaframe_b200.multigpu import rank_frames
+    spp_total = args.c5_spp
+    if rank == 0:
+        ensure_pack("c4_stress")
+    barrier()
+    pack = lf.ScenePack(ensure_pack("c4_stress"))
+    pt = lf.PathTracer(local_rank)
+    pt.set_stream(stream.cuda_stream)
+    pt.upload_pack(pack)
+    W, H = pt.params.width, pt.params.height
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(pt.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        pt.nccl_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    f0, n, st = rank_frames(2, spp_total, rank, world)
+    chunk = 32
+    pt.render_frames(f0, min(chunk, n), st)            # warm-up (kernels, clocks), then the collective
+    if world > 1:
+        pt.reduce()
+    torch.cuda.synchronize()
+    pt.clear()
+    barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    done = 0
+    while done < n:
+        m = min(chunk, n - done)
+        pt.render_frames(f0 + done * st, m, st)
+        done += m
+    if world > 1:
+        pt.reduce()
+    e1.record(stream)
+    torch.cuda.synchronize(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    img = pt.read_accum() if rank == 0 else None
+    pt.close()
+    rec = {"workload": WORKLOADS["c4_stress"][1], "resolution": [W, H], "spp_total": spp_total, "spp_per_rank": n, "n_gpus": world, "scaling": "strong",
+           "seconds": ms * 1e-3, "value": W * H * spp_total / (ms * 1e-3), "unit": "samples/s",
+           "collective": "lfcuda_reduce (ncclAllReduce, fp32 sum of the 3840x2160x3 accumulation buffer) inside the timed region" if world > 1 else "none (single GPU)"}
+    if rank == 0:
+        m = img / np.float32(spp_total)
+        rec["mean_rgb"] = [float(x) for x in m.mean(axis=(0, 1))]
+        rec["finite"] = bool(np.isfinite(img).all())
+    return rec
 
 
 if __name__ == "__main__":

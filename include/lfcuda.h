@@ -218,6 +218,36 @@ int  lfcuda_nccl_init(lfcuda_ctx* ctx, const void* id128, int32_t rank, int32_t 
 /* ncclAllReduce(sum, float32) of the accumulation buffer, in place, on the context's stream. */
 int  lfcuda_reduce(lfcuda_ctx* ctx);
 
+/* ---- multi-GPU in one process: a group of contexts behind one renderer --------------------------------------------------
+ * The reference constructs ONE renderer (LavaFrame/Main.cpp:88-97); CudaRenderer(scene, dir, devices) therefore drives several GPUs
+ * from one process through a group: one context + one host thread per device, the scene replicated, the frames of every render
+ * call dealt round-robin to the devices (same spp split as above), and the devices' accumulation buffers summed INSIDE the
+ * post-process kernel of the group's first device, which reads the peers' buffers over NVLink through CUDA peer access
+ * (no NCCL, no staging buffer, the local sums stay local so rendering continues after a read-out).
+ * Replaces what SURVEY 8(b) sketched as lfcuda_create(ctx**, const int* devices, int ndev). */
+typedef struct lfcuda_group lfcuda_group;
+int  lfcuda_group_create(lfcuda_group** out, const int32_t* devices, int32_t ndev);   /* 1 <= ndev <= 16 */
+void lfcuda_group_destroy(lfcuda_group* g);
+const char* lfcuda_group_last_error(const lfcuda_group* g);                           /* g may be NULL: error of the last failed create */
+int  lfcuda_group_size(const lfcuda_group* g);
+lfcuda_ctx* lfcuda_group_ctx(lfcuda_group* g, int32_t index);                         /* the context of device `index` (preview, probes, counters) */
+int  lfcuda_group_upload_scene(lfcuda_group* g, const LfSceneView* scene);            /* every device, in parallel */
+int  lfcuda_group_update_instances(lfcuda_group* g, const float* transforms, int32_t num_instances,
+                                   const float* materials, int32_t num_materials,
+                                   const float* tlas_nodes, int32_t first_node, int32_t num_tlas_nodes);
+int  lfcuda_group_set_params(lfcuda_group* g, const LfParams* params);
+int  lfcuda_group_set_camera(lfcuda_group* g, const LfCamera* camera);
+int  lfcuda_group_set_post(lfcuda_group* g, const LfPostParams* post);
+int  lfcuda_group_clear(lfcuda_group* g);
+int  lfcuda_group_synchronize(lfcuda_group* g);
+/* lfcuda_render_frames for the group: device i of n renders frames first + i*stride, first + (i+n)*stride, ...  Asynchronous. */
+int  lfcuda_group_render_frames(lfcuda_group* g, int32_t first_frame, int32_t nframes, int32_t frame_stride,
+                                int32_t tile_x, int32_t tile_y);
+/* lfcuda_read_output[_u8] / lfcuda_read_accum of the SUM of the devices' accumulation buffers (added in device order). */
+int  lfcuda_group_read_output(lfcuda_group* g, float inv_sample_counter, int32_t tonemap_index, float* rgb_out);
+int  lfcuda_group_read_output_u8(lfcuda_group* g, float inv_sample_counter, int32_t tonemap_index, uint8_t* rgb_out);
+int  lfcuda_group_read_accum(lfcuda_group* g, float* rgb_out);
+
 /* ---- instrumentation -------------------------------------------------------------------------------- */
 int  lfcuda_reset_counters(lfcuda_ctx* ctx);
 int  lfcuda_get_counters(lfcuda_ctx* ctx, LfCounters* out);
@@ -229,6 +259,12 @@ int  lfcuda_get_launch_count(lfcuda_ctx* ctx, uint64_t* out);
  * read-only loads over a `bytes`-sized buffer by a full grid; GB/s of the best pass.  A working set well below the
  * L2 size measures L2 -> SM bandwidth, one far above it measures HBM reads. */
 int  lfcuda_measure_read_bandwidth(lfcuda_ctx* ctx, size_t bytes, int32_t iters, double* gbps_out);
+
+/* Node-fetch probe: the rate (GB/s of 64-byte records) at which this GPU delivers one-record-per-lane fetches issued exactly like the
+ * traversal's inner-node fetch (2 x 256-bit read-only loads, every lane a different record, dependent chain) from a table of
+ * `table_bytes` (8 MiB: L2 hits; 32 KiB: L1 hits).  This is the ceiling of the bound ncu names for the extend kernel (L1 data-pipe
+ * wavefronts), measured in the run instead of read from a file. */
+int  lfcuda_measure_node_fetch(lfcuda_ctx* ctx, size_t table_bytes, int32_t iters, double* gbps_out);
 
 #ifdef __cplusplus
 }

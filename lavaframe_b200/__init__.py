@@ -7,8 +7,8 @@ glue used by the tests, `bench.py` and `__graft_entry__.py`; there is no Python 
 from .capi import (LfSceneView, LfParams, LfCamera, LfPostParams, LfCounters, LfStageStats, load_lfcuda, load_lfhost, LfCudaError,
                    STAGE_NAMES)
 from .scenepack import ScenePack
-from .pathtracer import PathTracer
+from .pathtracer import PathTracer, PathTracerGroup
 from .host import HostScene, CudaRenderer
 
 __all__ = ["LfSceneView", "LfParams", "LfCamera", "LfPostParams", "LfCounters", "LfStageStats", "load_lfcuda", "load_lfhost",
-           "LfCudaError", "STAGE_NAMES", "ScenePack", "PathTracer", "HostScene", "CudaRenderer"]
+           "LfCudaError", "STAGE_NAMES", "ScenePack", "PathTracer", "PathTracerGroup", "HostScene", "CudaRenderer"]

@@ -87,6 +87,23 @@ LFCUDA_SYMBOLS = {
     "lfcuda_clear": (C.c_int, [C.c_void_p]),
     "lfcuda_render_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "lfcuda_render_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lfcuda_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32]),
+    "lfcuda_group_destroy": (None, [C.c_void_p]),
+    "lfcuda_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "lfcuda_group_size": (C.c_int, [C.c_void_p]),
+    "lfcuda_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "lfcuda_group_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(LfSceneView)]),
+    "lfcuda_group_update_instances": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32]),
+    "lfcuda_group_set_params": (C.c_int, [C.c_void_p, C.POINTER(LfParams)]),
+    "lfcuda_group_set_camera": (C.c_int, [C.c_void_p, C.POINTER(LfCamera)]),
+    "lfcuda_group_set_post": (C.c_int, [C.c_void_p, C.POINTER(LfPostParams)]),
+    "lfcuda_group_clear": (C.c_int, [C.c_void_p]),
+    "lfcuda_group_synchronize": (C.c_int, [C.c_void_p]),
+    "lfcuda_group_render_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lfcuda_group_read_output": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
+    "lfcuda_group_read_output_u8": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
+    "lfcuda_group_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lfcuda_measure_node_fetch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
     "lfcuda_read_preview": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "lfcuda_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lfcuda_read_output": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_void_p]),
@@ -152,6 +169,8 @@ def load_lfhost():
     lib.lfhost_set_camera_moving.argtypes = [C.c_void_p, C.c_int]
     lib.lfhost_renderer_create.restype = C.c_void_p
     lib.lfhost_renderer_create.argtypes = [C.c_void_p, C.c_int]
+    lib.lfhost_renderer_create_multi.restype = C.c_void_p
+    lib.lfhost_renderer_create_multi.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
     lib.lfhost_renderer_destroy.argtypes = [C.c_void_p]
     lib.lfhost_renderer_ok.argtypes = [C.c_void_p]
     lib.lfhost_renderer_error.restype = C.c_char_p

@@ -108,13 +108,31 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refill from the queue
 constexpr int kLeafGather = LF_LEAF_GATHER;   // leaf phase starts when live lanes / kLeafGather are parked at a leaf
 
-template <bool ANY, bool CULL, bool COUNT, int STACK>
+// Shared-memory budget of a traversal CTA.  LF_SH_STACK entries of every thread's stack live in shared memory, deeper entries in the
+// global overflow array (lf_device.cuh SplitStk); with LF_WRAY_SHARED = 0 the world-space ray is re-read from the path state when a
+// BLAS is left (0.6 - 1.8 times per ray) instead of being parked in shared memory.  Both exist to give the SM's unified L1 / shared
+// array back to the L1: 9 CTAs x (16 KB stack + 4.5 KB ray) forced the 228 KB carve-out, i.e. a 28 KB L1 under a walk whose bound
+// is the L1 data pipe.
+#ifndef LF_SH_STACK
+#define LF_SH_STACK 12
+#endif
+#ifndef LF_WRAY_SHARED
+#define LF_WRAY_SHARED 0
+#endif
+constexpr int kShStack = LF_SH_STACK;
+constexpr int kOvfEntries = 64 - kShStack;              // the reference's stack holds 64 (closest_hit.glsl:70); deeper scenes are refused at upload
+
+template <bool ANY, bool CULL, bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
-                                                       int* cursor, DevCounters* cnt) {
-    __shared__ int stack[STACK * kBlockThreads];
+                                                       int* cursor, int* __restrict__ overflow, DevCounters* cnt) {
+    __shared__ int stack[kShStack * kBlockThreads];
+    SplitStk<kShStack> stk;
+    stk.col = stack + threadIdx.x;
+    stk.ovfBase = overflow;
+#if LF_WRAY_SHARED
     __shared__ float wray[9 * kBlockThreads];           // world-space ray of each lane + 1/direction (restored when a BLAS is left)
-    int* stk = stack + threadIdx.x;
     float* wr = wray + threadIdx.x;
+#endif
     const int count = *countp;
     const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
     constexpr unsigned FULL = 0xffffffffu;
@@ -130,19 +148,6 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
     w.o = w.d = w.idir = mk3(0.f);
     hit_clear(hit);
 
-    auto world_ray = [&]() { Ray r; r.o = mk3(wr[0], wr[kBlockThreads], wr[2 * kBlockThreads]);
-                             r.d = mk3(wr[3 * kBlockThreads], wr[4 * kBlockThreads], wr[5 * kBlockThreads]); return r; };
-    // start the walk of ray r; returns false when the ray is already decided (ANY: an analytic light blocks it)
-    auto begin_ray = [&](const Ray& r) -> bool {
-        wr[0] = r.o.x; wr[kBlockThreads] = r.o.y; wr[2 * kBlockThreads] = r.o.z;
-        wr[3 * kBlockThreads] = r.d.x; wr[4 * kBlockThreads] = r.d.y; wr[5 * kBlockThreads] = r.d.z;
-        if (!ANY) hit_clear(hit);
-        bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
-        if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return false;
-        walk_begin(S, r, w, stk);
-        wr[6 * kBlockThreads] = w.idir.x; wr[7 * kBlockThreads] = w.idir.y; wr[8 * kBlockThreads] = w.idir.z;
-        return true;
-    };
     // shadow: load NEE ray `phase` of the slot
     auto shadow_ray = [&](int phase) {
         float4 so = A.sh_o[slot];
@@ -150,6 +155,31 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         Ray r; r.o = xyz(so); r.d = xyz(dd);
         maxDist = dd.w;
         return r;
+    };
+#if LF_WRAY_SHARED
+    auto world_ray = [&]() { Ray r; r.o = mk3(wr[0], wr[kBlockThreads], wr[2 * kBlockThreads]);
+                             r.d = mk3(wr[3 * kBlockThreads], wr[4 * kBlockThreads], wr[5 * kBlockThreads]); return r; };
+#else
+    // the world-space ray of this lane, re-read from the path state it was started from (same bits: begin_ray only copied it)
+    auto world_ray = [&]() { Ray r;
+                             if (ANY) { float4 so = A.sh_o[slot]; float4 dd = shPhase == 0 ? A.sh_d0[slot] : A.sh_d1[slot]; r.o = xyz(so); r.d = xyz(dd); }
+                             else { r.o = xyz(A.ray_o[slot]); r.d = xyz(A.ray_d[slot]); }
+                             return r; };
+#endif
+    // start the walk of ray r; returns false when the ray is already decided (ANY: an analytic light blocks it)
+    auto begin_ray = [&](const Ray& r) -> bool {
+#if LF_WRAY_SHARED
+        wr[0] = r.o.x; wr[kBlockThreads] = r.o.y; wr[2 * kBlockThreads] = r.o.z;
+        wr[3 * kBlockThreads] = r.d.x; wr[4 * kBlockThreads] = r.d.y; wr[5 * kBlockThreads] = r.d.z;
+#endif
+        if (!ANY) hit_clear(hit);
+        bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
+        if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return false;
+        walk_begin(S, r, w, stk);
+#if LF_WRAY_SHARED
+        wr[6 * kBlockThreads] = w.idir.x; wr[7 * kBlockThreads] = w.idir.y; wr[8 * kBlockThreads] = w.idir.z;
+#endif
+        return true;
     };
 
     for (;;) {
@@ -202,9 +232,13 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                     w.inBlas = false;
                     Ray r = world_ray();
                     w.o = r.o; w.d = r.d;
+#if LF_WRAY_SHARED
                     w.idir = mk3(wr[6 * kBlockThreads], wr[7 * kBlockThreads], wr[8 * kBlockThreads]);
+#else
+                    w.idir = mk3(1.0f) / r.d;                // the same quotient walk_begin formed
+#endif
                     w.axis = has_inf(w.idir);
-                    w.ref = stk[(--w.sp) * kBlockThreads];
+                    w.ref = stk.pop(w.sp);
                 }
             } else {
                 Ray r = world_ray();
@@ -215,7 +249,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         // ---- phase 2b: the parked leaves' triangles, together
         if (alive && !rayDone && w.ref < 0 && !(w.ref & kRefTlasBit)) {
             if (walk_leaf<ANY, COUNT>(S, w, maxDist, hit, cnt)) { rayDone = true; hit.light = 0; }      // ANY: occluded
-            else w.ref = stk[(--w.sp) * kBlockThreads];
+            else w.ref = stk.pop(w.sp);
         }
         __syncwarp();
         // ---- finished rays: write the result; shadow lanes go on with their second ray
@@ -447,6 +481,29 @@ __global__ void k_post(const float* __restrict__ accum, float* out_f, unsigned c
     }
 }
 
+// The same pass over the accumulation buffers of a multi-GPU group (lf_post.cuh AccumSum): pixel i of the output is the post-processed
+// SUM of the devices' buffers.  Launched on the group's first device; the other devices' buffers are read through peer access (NVLink).
+// `sum_out` (optional) receives the plain sum, i.e. what lfcuda_read_accum returns for the group.
+__global__ void k_post_sum(AccumSum accum, float* out_f, unsigned char* out_u8, float* sum_out, int W, int H, float inv, int tonemap, LfPostParams pp) {
+    const int n = W * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (sum_out) { sum_out[3 * i] = accum[3 * (size_t)i]; sum_out[3 * i + 1] = accum[3 * (size_t)i + 1]; sum_out[3 * i + 2] = accum[3 * (size_t)i + 2]; }
+        if (!out_f && !out_u8) continue;
+        float c[3];
+        post_pixel(accum, W, H, i, inv, tonemap, pp, c);
+        if (out_f) { out_f[3 * i] = c[0]; out_f[3 * i + 1] = c[1]; out_f[3 * i + 2] = c[2]; }
+        if (out_u8)
+            for (int k = 0; k < 3; k++) out_u8[3 * i + k] = (unsigned char)__float2int_rn(clampf(c[k], 0.0f, 1.0f) * 255.0f);
+    }
+}
+void launch_post_sum(cudaStream_t stream, const float* const* accums, int naccum, float* out_f, unsigned char* out_u8, float* sum_out, int W, int H,
+                     float inv, int tonemap, const LfPostParams& pp) {
+    AccumSum a;
+    a.n = naccum;
+    for (int k = 0; k < kMaxGroup; k++) a.p[k] = k < naccum ? accums[k] : nullptr;
+    k_post_sum<<<(W * H + 255) / 256, 256, 0, stream>>>(a, out_f, out_u8, sum_out, W, H, inv, tonemap, pp);
+}
+
 // ---------------------------------------------------------------------------------------------- bandwidth probe
 // 16-byte read-only loads (LDG.E.128.CONSTANT, the load the traversal uses) over a buffer, 4 independent loads in
 // flight per thread; the xor-sum keeps the loads alive.
@@ -467,21 +524,56 @@ void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int pa
     k_read_probe<<<blocks, 256, 0, stream>>>(buf, n4, passes, sink);
 }
 
+// Node-fetch probe (the bound ncu names for the traversal: L1 data-pipe wavefronts).  Every lane walks its own pseudo-random chain
+// of 64-byte records fetched exactly like walk_step fetches an inner node (2 x LDG.E.ENL2.256 per record, every lane a different
+// record, the next index depending on the loaded data), 8 CTAs x 128 threads per SM, nothing else in the loop.  The rate it reaches
+// over a table that fits L2 is the ceiling of one-node-per-lane traversal on this GPU (tools/l1_probe.cu has the other variants).
+__global__ void __launch_bounds__(128, 8) k_node_probe(const float4* __restrict__ nodes, unsigned mask, int steps, unsigned* sink) {
+    unsigned idx = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+    float acc = 0.f;
+    for (int s = 0; s < steps; s++) {
+        const float4* p = nodes + (size_t)4 * ((idx >> 7) & mask);
+        f8 x = ldg8(p), y = ldg8(p + 2);
+        acc += ((x.lo.x + x.lo.y) + (x.lo.z + x.lo.w)) + ((x.hi.x + x.hi.y) + (x.hi.z + x.hi.w)) + ((y.lo.x + y.lo.y) + (y.lo.z + y.lo.w)) +
+               ((y.hi.x + y.hi.y) + (y.hi.z + y.hi.w));
+        idx = idx * 1664525u + 1013904223u + __float_as_uint(y.hi.w);
+    }
+    if (acc == 123.456f) *sink = 1;
+}
+void launch_node_probe(cudaStream_t stream, const float4* nodes, unsigned num_nodes_pow2, int steps, unsigned* sink, int blocks) {
+    k_node_probe<<<blocks, 128, 0, stream>>>(nodes, num_nodes_pow2 - 1u, steps, sink);
+}
+
 // ---------------------------------------------------------------------------------------------- launchers
-template <bool CULL, bool COUNT, int STACK>
-static void launch_trace_kernels_t(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
-    if (which == 0) k_trace<false, CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
-    else k_trace<true, CULL, COUNT, STACK><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+// The kernel's shared memory is static and small; ask for the smallest carve-out that holds the resident CTAs so that the rest of the
+// SM's 256 KB array serves as L1 (the default heuristic may reserve more shared memory than the kernel can ever use).
+template <class K>
+static void prefer_l1(K kernel, int ctas_per_sm) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return; }
+    const size_t need = (size_t)ctas_per_sm * (fa.sharedSizeBytes + 1024);           // + the 1 KB the system reserves per CTA
+    int pct = (int)((need * 100 + (size_t)228 * 1024 - 1) / ((size_t)228 * 1024));
+    if (pct > 100) pct = 100;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
+}
+// once per context (function attributes are per device)
+void configure_trace_kernels(int ctas_per_sm) {
+    prefer_l1(k_trace<false, true, false>, ctas_per_sm); prefer_l1(k_trace<true, true, false>, ctas_per_sm);
+    prefer_l1(k_trace<false, false, false>, ctas_per_sm); prefer_l1(k_trace<true, false, false>, ctas_per_sm);
+    prefer_l1(k_trace<false, true, true>, ctas_per_sm); prefer_l1(k_trace<true, true, true>, ctas_per_sm);
+    prefer_l1(k_trace<false, false, true>, ctas_per_sm); prefer_l1(k_trace<true, false, true>, ctas_per_sm);
 }
 template <bool CULL, bool COUNT>
 static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
-    if (L.stack_depth <= 32) launch_trace_kernels_t<CULL, COUNT, 32>(L, which, queue, countp, cursor);
-    else launch_trace_kernels_t<CULL, COUNT, 64>(L, which, queue, countp, cursor);
+    if (which == 0) k_trace<false, CULL, COUNT><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.stack_overflow, L.counters);
+    else k_trace<true, CULL, COUNT><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.stack_overflow, L.counters);
 }
 static void launch_trace(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
     if (L.cull) { if (L.count) launch_trace_kernels_s<true, true>(L, which, queue, countp, cursor); else launch_trace_kernels_s<true, false>(L, which, queue, countp, cursor); }
     else { if (L.count) launch_trace_kernels_s<false, true>(L, which, queue, countp, cursor); else launch_trace_kernels_s<false, false>(L, which, queue, countp, cursor); }
 }
+
+int trace_overflow_entries() { return kOvfEntries; }
 
 void launch_generate(const LaunchCtx& L) {
     int total = L.params.num_frames * L.params.slots_per_frame;

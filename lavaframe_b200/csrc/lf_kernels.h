@@ -30,7 +30,10 @@ struct LaunchCtx {
     int stack_depth;         // traversal stack entries the scene needs (<= 64)
     bool cull, count;
     const SortCtx* sort = nullptr;   // non-null = sort the extend queue of bounces >= 1
+    int* stack_overflow = nullptr;   // traversal stack entries beyond the shared-memory part: [trace_overflow_entries()][persistent threads]
 };
+int trace_overflow_entries();
+void configure_trace_kernels(int ctas_per_sm);   // shared-memory carve-out of the traversal kernels on the current device
 
 void launch_generate(const LaunchCtx& L);
 void launch_extend(const LaunchCtx& L, int depth);
@@ -41,7 +44,11 @@ void launch_accumulate(const LaunchCtx& L, float* accum);
 void launch_preview_store(const LaunchCtx& L, float* preview);
 void launch_megakernel(const LaunchCtx& L);
 void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* emitter);
+void launch_node_probe(cudaStream_t stream, const float4* nodes, unsigned num_nodes_pow2, int steps, unsigned* sink, int blocks);
 void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int passes, float* sink, int blocks);
+constexpr int kMaxGroupDevices = 16;
+void launch_post_sum(cudaStream_t stream, const float* const* accums, int naccum, float* out_f, unsigned char* out_u8, float* sum_out, int W, int H,
+                     float inv, int tonemap, const LfPostParams& pp);
 void launch_post(cudaStream_t stream, const float* accum, float* out_f, unsigned char* out_u8, int W, int H, float inv, int tonemap, const LfPostParams& pp);
 
 }  // namespace lf

@@ -19,9 +19,28 @@ LFD float tm_uncharted(float c) {                                               
     const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
     return fdiv(c * (A * c + C * B) + D * E, c * (A * c + B) + D * F) - fdiv(E, F);
 }
+// Where the accumulated sum comes from.  AccumOne: one buffer (a single context).  AccumSum: the buffers of the contexts of a
+// multi-GPU group (spp split: every device holds the sum of ITS frames); the pass reads all of them - peers over NVLink by plain
+// loads through peer access - and adds them in device order, so the all-device image is formed inside the post-process pass itself
+// and never stored: the reduce and the tonemap are one kernel.
+constexpr int kMaxGroup = 16;
+struct AccumOne {
+    const float* p;
+    LFD float operator[](size_t i) const { return p[i]; }
+};
+struct AccumSum {
+    const float* p[kMaxGroup];
+    int n;
+    LFD float operator[](size_t i) const {
+        float s = p[0][i];
+        for (int k = 1; k < n; k++) s = s + p[k][i];
+        return s;
+    }
+};
 // accumTexture is LINEAR / MIRRORED_REPEAT (TiledRenderer.cpp:165-173): bilinear fetch at a normalised coordinate
 LFD int mirrori(int i, int n) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
-LFD float accum_linear(const float* __restrict__ accum, int W, int H, float u, float v, int ch) {
+template <class A>
+LFD float accum_linear(const A& accum, int W, int H, float u, float v, int ch) {
     float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float wx = x - fx, wy = y - fy;
@@ -33,7 +52,8 @@ LFD float accum_linear(const float* __restrict__ accum, int W, int H, float u, f
 }
 
 // main() of postprocess.glsl for pixel i of a W x H image (rows bottom-up): c = the colour written to the output texture
-LFD void post_pixel(const float* __restrict__ accum, int W, int H, int i, float inv, int tonemap, const LfPostParams& pp, float c[3]) {
+template <class A>
+LFD void post_pixel(const A& accum, int W, int H, int i, float inv, int tonemap, const LfPostParams& pp, float c[3]) {
     const int px = i % W, py = i / W;
     const float tu = ((float)px + 0.5f) / (float)W, tv = ((float)py + 0.5f) / (float)H;   // TexCoords of the fullscreen quad
     c[0] = accum[3 * i] * inv; c[1] = accum[3 * i + 1] * inv; c[2] = accum[3 * i + 2] * inv;
@@ -66,6 +86,11 @@ LFD void post_pixel(const float* __restrict__ accum, int W, int H, int i, float 
         float d = 1.0f - lf_pow(sqrtf(dx * dx + dy * dy), pp.vignette_power) * pp.vignette_intensity;
         for (int k = 0; k < 3; k++) c[k] *= d;
     }
+}
+
+LFD void post_pixel(const float* accum, int W, int H, int i, float inv, int tonemap, const LfPostParams& pp, float c[3]) {
+    AccumOne a; a.p = accum;
+    post_pixel(a, W, H, i, inv, tonemap, pp, c);
 }
 
 }  // namespace lf

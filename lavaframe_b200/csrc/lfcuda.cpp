@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 
+#include "lf_ctx_internal.h"
 #include "lf_kernels.h"
 #include "lf_repack.h"
 
@@ -83,6 +84,7 @@ struct lfcuda_ctx {
     float* d_preview = nullptr; float* d_preview_out = nullptr;   // preview engine target (pathTraceTextureLowRes) + its post-processed copy
     size_t preview_cap = 0; int preview_w = 0, preview_h = 0;
     DevCounters* d_counters = nullptr;
+    int* d_stack_overflow = nullptr;      // traversal stack entries beyond the shared-memory part, [trace_overflow_entries()][persistent threads]
 
     // instrumentation
     bool profiling = false;
@@ -324,9 +326,9 @@ int check_ready(lfcuda_ctx* ctx) {
 void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
     L.scene = c->dev; L.params = D; L.soa = c->soa; L.queues = c->queues; L.counters = c->d_counters; L.stream = c->stream;
     L.sm_count = c->prop.multiProcessorCount;
-    // the 64-entry stack variant needs 38.4 KB of shared memory per CTA: 5 CTAs per SM are resident, not 9
-    L.persistent_blocks = L.sm_count * (c->packed.stack_depth > 32 ? std::min(c->ctas_per_sm, 5) : c->ctas_per_sm);
+    L.persistent_blocks = L.sm_count * c->ctas_per_sm;
     L.stack_depth = c->packed.stack_depth;
+    L.stack_overflow = c->d_stack_overflow;
     L.cull = !c->params.no_cull;
     L.count = c->params.count_work != 0;
     L.sort = (c->sort_rays && c->sort.sorted) ? &c->sort : nullptr;
@@ -383,6 +385,17 @@ constexpr int kNcclFloat32 = 7, kNcclSum = 0;
 
 }  // namespace
 
+namespace lf {
+bool ctx_view(lfcuda_ctx* c, CtxView* v) {
+    if (!c || !c->have_params || !c->d_accum) return false;
+    v->device = c->device; v->stream = c->stream; v->accum = c->d_accum; v->accum_floats = c->accum_floats;
+    v->out_f = c->d_out_f; v->out_u8 = c->d_out_u8; v->width = c->params.width; v->height = c->params.height; v->post = c->post;
+    return true;
+}
+void ctx_count_launch(lfcuda_ctx* c) { c->launches++; }
+int ctx_fail(lfcuda_ctx* c, int code, const char* msg) { return fail(c, code, "%s", msg); }
+}  // namespace lf
+
 extern "C" {
 
 int lfcuda_abi_version(void) { return LFCUDA_ABI_VERSION; }
@@ -411,6 +424,17 @@ int lfcuda_create(lfcuda_ctx** out, int device) {
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("LF_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) c->ctas_per_sm = v; }
+    {
+        const size_t threads = (size_t)c->prop.multiProcessorCount * c->ctas_per_sm * kBlockThreads;
+        cudaError_t e3 = cudaMalloc((void**)&c->d_stack_overflow, std::max<size_t>(1, (size_t)trace_overflow_entries()) * threads * sizeof(int));
+        if (e3 != cudaSuccess) {
+            fail(nullptr, LFCUDA_ENOMEM, "traversal stack overflow array: %s", cudaGetErrorString(e3));
+            cudaFree(c->d_counters); cudaStreamDestroy(c->own_stream);
+            delete c;
+            return LFCUDA_ENOMEM;
+        }
+        configure_trace_kernels(c->ctas_per_sm);
+    }
     if (const char* e = getenv("LF_SORT_RAYS")) { c->sort.mode = atoi(e) & 3; c->sort_rays = c->sort.mode != 0; }
     *out = c;
     return 0;
@@ -427,6 +451,7 @@ void lfcuda_destroy(lfcuda_ctx* c) {
     free_frame(c);
     if (c->queues.counts) cudaFree(c->queues.counts);
     cudaFree(c->d_counters);
+    cudaFree(c->d_stack_overflow);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -892,6 +917,43 @@ int lfcuda_measure_read_bandwidth(lfcuda_ctx* ctx, size_t bytes, int32_t iters, 
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, a, b));
             double gbps = (double)n4 * sizeof(float4) * passes / (ms * 1e6);
+            if (gbps > best) best = gbps;
+            ctx->launches++;
+        }
+        return 0;
+    };
+    int r = body();
+    cudaStreamSynchronize(ctx->stream);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    if (!r) *gbps_out = best;
+    return r;
+}
+
+int lfcuda_measure_node_fetch(lfcuda_ctx* ctx, size_t table_bytes, int32_t iters, double* gbps_out) {
+    if (!ctx || !gbps_out || table_bytes < 4096 || iters < 1) return fail(ctx, LFCUDA_EINVAL, "bad node-fetch probe arguments");
+    CK(cudaSetDevice(ctx->device));
+    unsigned nnodes = 1;
+    while ((size_t)nnodes * 2 * 64 <= table_bytes) nnodes *= 2;          // power of two records of 64 bytes
+    float4* buf = nullptr; unsigned* sink = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    double best = 0.0;
+    auto body = [&]() -> int {
+        CK(cudaMalloc((void**)&buf, (size_t)nnodes * 64));
+        CK(cudaMalloc((void**)&sink, sizeof(unsigned)));
+        CK(cudaMemsetAsync(buf, 0, (size_t)nnodes * 64, ctx->stream));
+        const int blocks = ctx->prop.multiProcessorCount * 8, steps = 2000;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        launch_node_probe(ctx->stream, buf, nnodes, 200, sink, blocks);   // warm-up
+        for (int it = 0; it < iters; it++) {
+            CK(cudaEventRecord(a, ctx->stream));
+            launch_node_probe(ctx->stream, buf, nnodes, steps, sink, blocks);
+            CK(cudaEventRecord(b, ctx->stream));
+            CK(cudaEventSynchronize(b));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            double gbps = (double)blocks * 128 * steps * 64 / (ms * 1e6);
             if (gbps > best) best = gbps;
             ctx->launches++;
         }

@@ -54,10 +54,14 @@ class CudaRenderer:
     """The C++ LavaFrame::CudaRenderer (lavaframe_b200/host/CudaRenderer.h), same methods as the reference's
     Renderer interface (LavaFrame/Renderer.h:71-117)."""
 
-    def __init__(self, scene, device=0):
+    def __init__(self, scene, device=0, devices=None):
         self.lib = scene.lib
         self.scene = scene
-        self.h = self.lib.lfhost_renderer_create(scene.h, device)
+        if devices is None:
+            self.h = self.lib.lfhost_renderer_create(scene.h, device)
+        else:   # several GPUs behind the one renderer (lfcuda_group_*)
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.h = self.lib.lfhost_renderer_create_multi(scene.h, arr, len(devices))
         if not self.lib.lfhost_renderer_ok(self.h):
             msg = self.lib.lfhost_renderer_error(self.h).decode()
             self.lib.lfhost_renderer_destroy(self.h)

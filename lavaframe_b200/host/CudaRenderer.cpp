@@ -18,8 +18,13 @@ extern LavaFrameState GlobalState;
 namespace LavaFrame
 {
     CudaRenderer::CudaRenderer(Scene* scene, const std::string& shadersDirectory, int device_)
+        : CudaRenderer(scene, shadersDirectory, std::vector<int>(1, device_))
+    {
+    }
+
+    CudaRenderer::CudaRenderer(Scene* scene, const std::string& shadersDirectory, const std::vector<int>& devices_)
         : Renderer(scene, shadersDirectory)
-        , ctx(nullptr), device(device_)
+        , group(nullptr), ctx(nullptr), devices(devices_)
         , tileX(-1), tileY(-1), numTilesX(-1), numTilesY(-1)
         , tileWidth(scene->renderOptions.tileWidth), tileHeight(scene->renderOptions.tileHeight)
         , currentBuffer(0), frameCounter(1), sampleCounter(0)
@@ -32,15 +37,16 @@ namespace LavaFrame
         this->Finish();                                      // frees the context whether or not Init completed
     }
 
-    const char* CudaRenderer::LastError() const { return ctx ? lfcuda_last_error(ctx) : error.c_str(); }
+    const char* CudaRenderer::LastError() const { return group ? lfcuda_group_last_error(group) : error.c_str(); }
 
     // Init failed after the context was created: keep the message, release the device, leave the renderer not initialised
     // (every entry point then returns at once, like the reference after a failed shader compile, Renderer.cpp:81-85).
     void CudaRenderer::FailInit()
     {
-        error = ctx ? lfcuda_last_error(ctx) : lfcuda_last_error(nullptr);
+        error = lfcuda_group_last_error(group);
         printf("CudaRenderer: %s\n", error.c_str());
-        if (ctx) lfcuda_destroy(ctx);
+        if (group) lfcuda_group_destroy(group);
+        group = nullptr;
         ctx = nullptr;
         initialized = false;
     }
@@ -64,12 +70,13 @@ namespace LavaFrame
         previewDepth = scene->renderOptions.maxDepth;
         previewW = previewH = 0;
 
-        if (lfcuda_create(&ctx, device) != 0) { ctx = nullptr; FailInit(); return; }
+        if (lfcuda_group_create(&group, devices.data(), (int)devices.size()) != 0) { group = nullptr; FailInit(); return; }
+        ctx = lfcuda_group_ctx(group, 0);
         LfSceneView view;
         lfhost::MakeSceneView(scene, &view);
-        if (lfcuda_upload_scene(ctx, &view) != 0) { FailInit(); return; }       // e.g. a BVH deeper than the 64-entry stack
-        if (!UploadUniforms()) { FailInit(); return; }                           // e.g. path state does not fit the device
-        if (lfcuda_clear(ctx) != 0) { FailInit(); return; }
+        if (lfcuda_group_upload_scene(group, &view) != 0) { FailInit(); return; }   // e.g. a BVH deeper than the 64-entry stack
+        if (!UploadUniforms()) { FailInit(); return; }                               // e.g. path state does not fit the device
+        if (lfcuda_group_clear(group) != 0) { FailInit(); return; }
         initialized = true;
     }
 
@@ -84,8 +91,8 @@ namespace LavaFrame
         post.use_ca = ro.useCA ? 1 : 0; post.use_ca_distortion = ro.useCADistortion ? 1 : 0;
         post.ca_distance = ro.caDistance; post.ca_p1 = ro.caP1; post.ca_p2 = ro.caP2; post.ca_p3 = ro.caP3;
         post.use_vignette = ro.useVignette ? 1 : 0; post.vignette_intensity = ro.vignetteIntensity; post.vignette_power = ro.vignettePower;
-        if (lfcuda_set_params(ctx, &params) != 0 || lfcuda_set_camera(ctx, &cam) != 0 || lfcuda_set_post(ctx, &post) != 0) {
-            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+        if (lfcuda_group_set_params(group, &params) != 0 || lfcuda_group_set_camera(group, &cam) != 0 || lfcuda_group_set_post(group, &post) != 0) {
+            printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
             return false;
         }
         return true;
@@ -94,7 +101,8 @@ namespace LavaFrame
     void CudaRenderer::Finish()
     {
         pending.clear();
-        if (ctx) lfcuda_destroy(ctx);
+        if (group) lfcuda_group_destroy(group);
+        group = nullptr;
         ctx = nullptr;
         if (initialized) Renderer::Finish();
         initialized = false;
@@ -108,8 +116,8 @@ namespace LavaFrame
             size_t j = i + 1;
             while (j < count && pending[j].tileX == pending[i].tileX && pending[j].tileY == pending[i].tileY &&
                    pending[j].frame == pending[j - 1].frame + 1) j++;
-            if (lfcuda_render_frames(ctx, pending[i].frame, (int)(j - i), 1, pending[i].tileX, pending[i].tileY) != 0)
-                printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+            if (lfcuda_group_render_frames(group, pending[i].frame, (int)(j - i), 1, pending[i].tileX, pending[i].tileY) != 0)
+                printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
             i = j;
         }
         pending.erase(pending.begin(), pending.begin() + count);
@@ -153,10 +161,10 @@ namespace LavaFrame
         if (scene->instancesModified) {          // Renderer::Update, Renderer.cpp:190-205
             int index = scene->bvhTranslator.topLevelIndex;
             int total = (int)scene->bvhTranslator.nodes.size();
-            if (lfcuda_update_instances(ctx, reinterpret_cast<const float*>(scene->transforms.data()), (int)scene->transforms.size(),
-                                        reinterpret_cast<const float*>(scene->materials.data()), (int)scene->materials.size(),
-                                        reinterpret_cast<const float*>(&scene->bvhTranslator.nodes[index]), index, total - index) != 0)
-                printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+            if (lfcuda_group_update_instances(group, reinterpret_cast<const float*>(scene->transforms.data()), (int)scene->transforms.size(),
+                                              reinterpret_cast<const float*>(scene->materials.data()), (int)scene->materials.size(),
+                                              reinterpret_cast<const float*>(&scene->bvhTranslator.nodes[index]), index, total - index) != 0)
+                printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
         }
         if (scene->camera->isMoving || scene->instancesModified) {   // TiledRenderer.cpp:471-484
             tileX = -1;
@@ -164,7 +172,7 @@ namespace LavaFrame
             sampleCounter = 1;
             frameCounter = 1;
             pending.clear();
-            lfcuda_clear(ctx);
+            lfcuda_group_clear(group);
         } else {                                                     // :485-501
             frameCounter++;
             tileX++;
@@ -202,8 +210,8 @@ namespace LavaFrame
         FlushCompletedSamples();
         int completed = sampleCounter - 1;                           // what tileOutputTexture[1 - currentBuffer] holds
         float inv = 1.0f / (float)(completed > 0 ? completed : 1);   // invSampleCounter, TiledRenderer.cpp:542
-        if (lfcuda_read_output(ctx, inv, scene->renderOptions.tonemapIndex, *data) != 0)
-            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+        if (lfcuda_group_read_output(group, inv, scene->renderOptions.tonemapIndex, *data) != 0)
+            printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
     }
 
     void CudaRenderer::GetOutputBuffer(unsigned char** data, int& w, int& h)
@@ -215,7 +223,7 @@ namespace LavaFrame
         FlushCompletedSamples();
         int completed = sampleCounter - 1;
         float inv = 1.0f / (float)(completed > 0 ? completed : 1);
-        if (lfcuda_read_output_u8(ctx, inv, scene->renderOptions.tonemapIndex, *data) != 0)
-            printf("CudaRenderer: %s\n", lfcuda_last_error(ctx));
+        if (lfcuda_group_read_output_u8(group, inv, scene->renderOptions.tonemapIndex, *data) != 0)
+            printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
     }
 }

@@ -25,6 +25,10 @@ namespace LavaFrame
     {
     public:
         CudaRenderer(Scene* scene, const std::string& shadersDirectory, int device = 0);
+        // Several GPUs behind the one renderer the application constructs (Main.cpp:91): one context + host thread per device,
+        // the frames of every batch dealt round-robin (spp split, disjoint RNG streams), the devices' accumulation buffers summed
+        // inside the post-process pass of devices[0] over NVLink peer access when an output buffer is asked for (lfcuda_group_*).
+        CudaRenderer(Scene* scene, const std::string& shadersDirectory, const std::vector<int>& devices);
         ~CudaRenderer();
 
         void Init() override;
@@ -40,7 +44,9 @@ namespace LavaFrame
         uint32_t Denoise() override { return 0; }                // OIDN is not part of the path
 
         // Extras for drivers/tests (not part of the reference interface)
-        lfcuda_ctx* Context() const { return ctx; }
+        lfcuda_ctx* Context() const { return ctx; }                 // the context of the first device (preview, probes)
+        lfcuda_group* Group() const { return group; }
+        int NumDevices() const { return (int)devices.size(); }
         bool Ok() const { return initialized && ctx != nullptr; }   // Init completed: scene uploaded, uniforms set, accumulation cleared
         const char* LastError() const;
         void Flush();                                            // execute every queued tile step now
@@ -56,8 +62,9 @@ namespace LavaFrame
         bool UploadUniforms();
         void FailInit();
 
-        lfcuda_ctx* ctx;
-        int device;
+        lfcuda_group* group;             // one context per device; a single-GPU renderer is a group of one
+        lfcuda_ctx* ctx;                 // = lfcuda_group_ctx(group, 0)
+        std::vector<int> devices;
         std::vector<Step> pending;       // tile steps requested by Render() and not yet launched
 
         int tileX, tileY, numTilesX, numTilesY, tileWidth, tileHeight;

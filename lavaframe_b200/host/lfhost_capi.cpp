@@ -2,6 +2,7 @@
 // CudaRenderer) so that the Python tests and bench.py can drive the real drop-in class through ctypes.
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "Scene.h"
 #include "Loader.h"
@@ -72,6 +73,14 @@ void lfhost_set_camera_moving(void* s, int moving) { static_cast<Scene*>(s)->cam
 void* lfhost_renderer_create(void* s, int device) {
     Scene* scene = static_cast<Scene*>(s);
     CudaRenderer* r = new CudaRenderer(scene, GlobalState.shadersDir, device);   // replaces `new TiledRenderer(...)`, Main.cpp:91
+    GlobalState.renderer = r;
+    r->Init();
+    return r;
+}
+// ... on several GPUs of this process (CudaRenderer(scene, dir, devices)); still the single construction of Main.cpp:91
+void* lfhost_renderer_create_multi(void* s, const int* devices, int ndev) {
+    Scene* scene = static_cast<Scene*>(s);
+    CudaRenderer* r = new CudaRenderer(scene, GlobalState.shadersDir, std::vector<int>(devices, devices + ndev));
     GlobalState.renderer = r;
     r->Init();
     return r;

@@ -2,7 +2,8 @@
 // load the scene with the reference's loader, construct the renderer, loop Update -> Render until
 // `maxSamples + 1 == GetSampleCount()` (Main.cpp:197), then fetch GetOutputBufferHDR.
 //
-//   lf_render <scene> --spp N [--out img.f32] [--png f.png] [--bmp f.bmp] [--tga f.tga] [--jpg f.jpg] [--device D] [--tonemap]
+//   lf_render <scene> --spp N [--out img.f32] [--png f.png] [--bmp f.bmp] [--tga f.tga] [--jpg f.jpg] [--device D | --gpus N | --devices a,b,..] [--tonemap]
+// --gpus N / --devices: the ONE renderer Main.cpp constructs drives several GPUs of this process (CudaRenderer(scene, dir, devices)).
 // img.f32: W*H*3 float32, rows bottom-up (the exporters flip, Export.h:19).  --png / --bmp / --tga / --jpg do what SaveFrame,
 // SaveFrameBMP, SaveFrameTGA and SaveFrameJPG do (LavaFrame/Export.h:14-57): GetOutputBuffer -> stbi_flip_vertically_on_write ->
 // stbi_write_*, with the reference's own stb_image_write.h compiled from where it lies.
@@ -11,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #define STB_IMAGE_WRITE_IMPLEMENTATION
 #include "stb_image_write.h"
@@ -26,7 +28,8 @@ extern LavaFrameState GlobalState;
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: lf_render <scene> --spp N [--out img.f32] [--device D] [--tonemap]\n"); return 2; }
     std::string out, png, bmp, tga, jpg;
-    int spp = 1, device = 0;
+    int spp = 1;
+    std::vector<int> devices(1, 0);
     bool keepTonemap = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
@@ -36,7 +39,9 @@ int main(int argc, char** argv) {
         else if (a == "--bmp") bmp = argv[++i];
         else if (a == "--tga") tga = argv[++i];
         else if (a == "--jpg") jpg = argv[++i];
-        else if (a == "--device") device = atoi(argv[++i]);
+        else if (a == "--device") devices.assign(1, atoi(argv[++i]));
+        else if (a == "--gpus") { int n = atoi(argv[++i]); devices.clear(); for (int d = 0; d < n; d++) devices.push_back(d); }
+        else if (a == "--devices") { devices.clear(); for (char* t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) devices.push_back(atoi(t)); }
         else if (a == "--tonemap") keepTonemap = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -49,7 +54,8 @@ int main(int argc, char** argv) {
     GlobalState.scene->renderOptions = ro;
     GlobalState.scene->camera->isMoving = false;
 
-    CudaRenderer* r = new CudaRenderer(GlobalState.scene, GlobalState.shadersDir, device);   // Main.cpp:91
+    if (devices.empty()) { fprintf(stderr, "lf_render: no devices\n"); return 2; }
+    CudaRenderer* r = new CudaRenderer(GlobalState.scene, GlobalState.shadersDir, devices);   // Main.cpp:91
     GlobalState.renderer = r;
     r->Init();
     if (!r->Ok()) { fprintf(stderr, "lf_render: %s\n", r->LastError()); return 3; }
@@ -68,8 +74,8 @@ int main(int argc, char** argv) {
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     double sum[3] = {0, 0, 0};
     for (long i = 0; i < (long)w * h; i++) for (int k = 0; k < 3; k++) sum[k] += img[3 * i + k];
-    printf("{\"impl\": \"cuda\", \"width\": %d, \"height\": %d, \"spp\": %d, \"tile_steps\": %d, \"seconds\": %.4f, \"samples_per_s\": %.1f, "
-           "\"mean_rgb\": [%.8g, %.8g, %.8g]}\n", w, h, spp, steps, sec, (double)w * h * spp / sec, sum[0] / (w * h), sum[1] / (w * h), sum[2] / (w * h));
+    printf("{\"impl\": \"cuda\", \"gpus\": %d, \"width\": %d, \"height\": %d, \"spp\": %d, \"tile_steps\": %d, \"seconds\": %.4f, \"samples_per_s\": %.1f, "
+           "\"mean_rgb\": [%.8g, %.8g, %.8g]}\n", (int)devices.size(), w, h, spp, steps, sec, (double)w * h * spp / sec, sum[0] / (w * h), sum[1] / (w * h), sum[2] / (w * h));
     if (!out.empty()) { FILE* f = fopen(out.c_str(), "wb"); fwrite(img, 4, (size_t)w * h * 3, f); fclose(f); }
     delete[] img;
     if (!png.empty() || !bmp.empty() || !tga.empty() || !jpg.empty()) {   // Export.h:14-57

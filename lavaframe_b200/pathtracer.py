@@ -171,6 +171,11 @@ class PathTracer:
         self._ck(self.lib.lfcuda_measure_read_bandwidth(self.h, int(nbytes), int(iters), C.byref(g)), "lfcuda_measure_read_bandwidth")
         return float(g.value)
 
+    def measure_node_fetch(self, table_bytes=8 << 20, iters=5):
+        g = C.c_double()
+        self._ck(self.lib.lfcuda_measure_node_fetch(self.h, int(table_bytes), int(iters), C.byref(g)), "lfcuda_measure_node_fetch")
+        return float(g.value)
+
     def launch_count(self):
         n = C.c_uint64()
         self._ck(self.lib.lfcuda_get_launch_count(self.h, C.byref(n)), "lfcuda_get_launch_count")
@@ -193,3 +198,82 @@ def algorithmic_bytes_total(c):
     """Traversal bytes + shading (160 B per shaded hit, 16 B per texture sample), env NEE (80 B), env miss (48 B)
     and the accumulate read+write (24 B per pixel-sample)."""
     return (algorithmic_bytes(c) + 160 * c["shaded_hits"] + 16 * c["tex_samples"] + 80 * c["env_nee"] + 48 * c["env_miss"] + 24 * c["samples"])
+
+
+class PathTracerGroup:
+    """Several GPUs behind one renderer in ONE process (lfcuda_group_*): one context + host thread per device, frames dealt
+    round-robin, the devices' accumulation buffers summed inside the post-process kernel of the first device over peer access."""
+
+    def __init__(self, devices):
+        self.lib = load_lfcuda()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.lfcuda_group_create(C.byref(h), devs, len(devices))
+        if rc != 0:
+            raise LfCudaError(f"lfcuda_group_create({list(devices)}) failed ({rc}): {self.lib.lfcuda_group_last_error(None).decode()}")
+        self.h = h
+        self.devices = list(devices)
+        self.params = None
+        self._keep = None
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise LfCudaError(f"{what} failed ({rc}): {self.lib.lfcuda_group_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lfcuda_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_pack(self, pack, **overrides):
+        self._keep = pack
+        view = pack.view()
+        self._ck(self.lib.lfcuda_group_upload_scene(self.h, C.byref(view)), "lfcuda_group_upload_scene")
+        p = pack.params()
+        for k, v in overrides.items():
+            setattr(p, k, v)
+        self.set_params(p)
+        cam = pack.camera()
+        self._ck(self.lib.lfcuda_group_set_camera(self.h, C.byref(cam)), "lfcuda_group_set_camera")
+
+    def set_params(self, p):
+        self._ck(self.lib.lfcuda_group_set_params(self.h, C.byref(p)), "lfcuda_group_set_params")
+        q = LfParams()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(LfParams))
+        self.params = q
+
+    def set_post(self, post=None):
+        self._ck(self.lib.lfcuda_group_set_post(self.h, C.byref(post) if post is not None else None), "lfcuda_group_set_post")
+
+    def clear(self):
+        self._ck(self.lib.lfcuda_group_clear(self.h), "lfcuda_group_clear")
+
+    def synchronize(self):
+        self._ck(self.lib.lfcuda_group_synchronize(self.h), "lfcuda_group_synchronize")
+
+    def render_frames(self, first_frame, nframes, frame_stride=1, tile_x=0, tile_y=0):
+        self._ck(self.lib.lfcuda_group_render_frames(self.h, first_frame, nframes, frame_stride, tile_x, tile_y), "lfcuda_group_render_frames")
+
+    def _shape(self):
+        return (self.params.height, self.params.width, 3)
+
+    def read_accum(self):
+        out = np.empty(self._shape(), np.float32)
+        self._ck(self.lib.lfcuda_group_read_accum(self.h, out.ctypes.data_as(C.c_void_p)), "lfcuda_group_read_accum")
+        return out
+
+    def read_output(self, inv_sample_counter, tonemap_index=0):
+        out = np.empty(self._shape(), np.float32)
+        self._ck(self.lib.lfcuda_group_read_output(self.h, float(inv_sample_counter), int(tonemap_index), out.ctypes.data_as(C.c_void_p)), "lfcuda_group_read_output")
+        return out
+
+    def read_output_u8(self, inv_sample_counter, tonemap_index=0):
+        out = np.empty(self._shape(), np.uint8)
+        self._ck(self.lib.lfcuda_group_read_output_u8(self.h, float(inv_sample_counter), int(tonemap_index), out.ctypes.data_as(C.c_void_p)), "lfcuda_group_read_output_u8")
+        return out

@@ -47,6 +47,18 @@ void lforacle_set_options(void* hv, int cull, int count) {
 void lforacle_render_frames(void* hv, int first_frame, int nframes, int frame_stride, int tile_x, int tile_y, float* accum) {
     static_cast<Handle*>(hv)->oracle->RenderFrames(first_frame, nframes, frame_stride, tile_x, tile_y, accum);
 }
+// OpenMP team size of the next parallel regions.  torchrun exports OMP_NUM_THREADS=1 to every rank; bench.py's reference arm
+// calls this with the host's core count so that the figure it reports is the one all host cores deliver.  Returns the team size in use.
+int lforacle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    int used = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        used = omp_get_num_threads();
+    }
+    return used;
+}
 void lforacle_render_preview(void* hv, int pv_w, int pv_h, int max_depth, int use_dof, float* out) {
     static_cast<Handle*>(hv)->oracle->RenderPreview(pv_w, pv_h, max_depth, use_dof != 0, out);
 }

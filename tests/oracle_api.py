@@ -42,6 +42,8 @@ def load_oracle():
     lib.lforacle_fp_flags.argtypes = [C.c_int]
     lib.lforacle_post_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     lib.lforacle_builtin_kat.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.lforacle_set_threads.restype = C.c_int
+    lib.lforacle_set_threads.argtypes = [C.c_int]
     lib.lforacle_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     lib.lforacle_reset_counters.argtypes = [C.c_void_p]
     _lib = lib
@@ -105,6 +107,11 @@ class Oracle:
         if self.h:
             self.lib.lforacle_close(self.h)
             self.h = None
+
+
+def set_threads(n=0):
+    """Set (n > 0) and return the OpenMP team size the oracle uses (torchrun exports OMP_NUM_THREADS=1)."""
+    return int(load_oracle().lforacle_set_threads(int(n)))
 
 
 def rand_kat(px, py, frame, n=4):

@@ -234,3 +234,64 @@ def test_headless_cxx_driver(golden_dir, gpu, tmp_path):
     assert info2["tile_steps"] == nt * (256 // tile) ** 2
     img2 = np.fromfile(out2, np.float32).reshape(256, 256, 3)
     assert radiance_agreement(img2, gt["sppN"]) >= 0.999
+
+
+def _device_lists():
+    import torch
+    n = torch.cuda.device_count()
+    lists = [[0, 0]]                                     # two contexts on one device: everything but the NVLink hop, on any box
+    if n >= 2:
+        lists.append([0, 1])
+    if n >= 8:
+        lists.append(list(range(8)))
+    return lists
+
+
+def test_multi_gpu_renderer_behind_the_single_construction(cornell_scene, golden_dir):
+    """CudaRenderer(scene, dir, devices): the ONE renderer Main.cpp:91 constructs drives several GPUs; Main.cpp's loop, the sample
+    counter and the output buffers behave as on one GPU, and the image equals the 1-GPU image up to fp32 summation order."""
+    n = 24
+    r1 = lf.CudaRenderer(cornell_scene)
+    r1.Run(n)
+    single = r1.GetOutputBufferHDR()
+    r1.close()
+    for devs in _device_lists():
+        r = lf.CudaRenderer(cornell_scene, devices=devs)
+        steps = r.Run(n)
+        assert steps == n and r.GetSampleCount() == n + 1
+        img = r.GetOutputBufferHDR()
+        np.testing.assert_allclose(img, single, rtol=2e-5, atol=1e-6)
+        u8 = r.GetOutputBuffer()
+        np.testing.assert_array_equal(u8, np.rint(np.clip(img, 0, 1) * 255).astype(np.uint8))
+        # progressive: more samples after a read-out, then a camera move resets every device
+        r.Run(n + 8)
+        r1 = lf.CudaRenderer(cornell_scene); r1.Run(n + 8)
+        np.testing.assert_allclose(r.GetOutputBufferHDR(), r1.GetOutputBufferHDR(), rtol=2e-5, atol=1e-6)
+        r1.close()
+        cornell_scene.set_camera_moving(True)
+        r.Update(0.0); r.Render()
+        assert r.GetSampleCount() == 1
+        cornell_scene.set_camera_moving(False)
+        r.Run(4)
+        r1 = lf.CudaRenderer(cornell_scene); r1.Run(4)
+        np.testing.assert_allclose(r.GetOutputBufferHDR(), r1.GetOutputBufferHDR(), rtol=2e-5, atol=1e-6)
+        r1.close()
+        r.close()
+
+
+def test_multi_gpu_renderer_instance_edit(cornell_scene, golden_dir, tmp_path, oracle_lib):
+    """The instance-edit path reaches every device of the group (lfcuda_group_update_instances)."""
+    pack = lf.ScenePack(os.path.join(golden_dir, "cornell.lfpack"))
+    m = pack.transforms.reshape(-1, 16)[3].copy()
+    for devs in _device_lists():
+        r = lf.CudaRenderer(cornell_scene, devices=devs)
+        r.Run(2)
+        moved = m.copy(); moved[13] += 0.1
+        cornell_scene.move_instance(3, moved)
+        r.Update(0.0); r.Render()
+        r.Run(6)
+        ref = _oracle_image(cornell_scene, tmp_path, "mg_moved", 6)
+        np.testing.assert_allclose(r.GetOutputBufferHDR(), ref, rtol=2e-5, atol=1e-6)
+        cornell_scene.move_instance(3, m)
+        r.Update(0.0); r.Render()
+        r.close()
