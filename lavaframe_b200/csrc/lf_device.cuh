@@ -237,35 +237,11 @@ LFD bool test_lights(const DevScene& S, const Ray& r, float maxDist, Hit& hit, D
 
 // A thread's traversal stack (the reference's `int stack[64]`, closest_hit.glsl:70).
 //   PlainStk       a column of a [depth][kBlockThreads] int array (megakernel: shared memory; tests/hostcheck: host memory)
-//   SplitStk<SH>   the first SH entries in the CTA's shared-memory array, deeper ones in a global-memory overflow array (k_trace).
-//                  With the distance cull 99.96 % of the rays of C2 / C4 never go past 12 entries (measured with the oracle), so the
-//                  shared-memory footprint of a traversal CTA drops from 16 KB (32 entries) to SH x 512 B, the SM's L1 carve-out
-//                  grows accordingly (28 KB -> 190 KB with 9 CTAs per SM), and the walk's upper levels stay resident in L1.
 struct PlainStk {
     int* col;
     LFD void push(int& sp, int v) const { col[sp * kBlockThreads] = v; sp++; }
     LFD int pop(int& sp) const { --sp; return col[sp * kBlockThreads]; }
 };
-template <int SH>
-struct SplitStk {
-    int* col;            // this thread's column of the shared-memory array [SH][kBlockThreads]
-    int* ovfBase;        // overflow array [64 - SH][threads of the grid] (a kernel parameter: costs no register; the thread's
-                         // column is worked out on the rare path only - the traversal kernels run at their register limit)
-#ifndef LF_HOST_CHECK
-    LFD int* ovf(int sp) const { return ovfBase + (size_t)(sp - SH) * (gridDim.x * kBlockThreads) + (blockIdx.x * kBlockThreads + threadIdx.x); }
-#else
-    LFD int* ovf(int sp) const { return ovfBase + (sp - SH); }
-#endif
-    LFD void push(int& sp, int v) const {
-        if (sp < SH) col[sp * kBlockThreads] = v; else *ovf(sp) = v;
-        sp++;
-    }
-    LFD int pop(int& sp) const {
-        --sp;
-        return sp < SH ? col[sp * kBlockThreads] : *ovf(sp);
-    }
-};
-
 template <class ST>
 LFD void walk_begin(const DevScene& S, const Ray& r, Walk& w, const ST& stk) {
     w.sp = 0;

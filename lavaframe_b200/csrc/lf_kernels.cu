@@ -108,31 +108,19 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refill from the queue
 constexpr int kLeafGather = LF_LEAF_GATHER;   // leaf phase starts when live lanes / kLeafGather are parked at a leaf
 
-// Shared-memory budget of a traversal CTA.  LF_SH_STACK entries of every thread's stack live in shared memory, deeper entries in the
-// global overflow array (lf_device.cuh SplitStk); with LF_WRAY_SHARED = 0 the world-space ray is re-read from the path state when a
-// BLAS is left (0.6 - 1.8 times per ray) instead of being parked in shared memory.  Both exist to give the SM's unified L1 / shared
-// array back to the L1: 9 CTAs x (16 KB stack + 4.5 KB ray) forced the 228 KB carve-out, i.e. a 28 KB L1 under a walk whose bound
-// is the L1 data pipe.
-#ifndef LF_SH_STACK
-#define LF_SH_STACK 12
-#endif
-#ifndef LF_WRAY_SHARED
-#define LF_WRAY_SHARED 0
-#endif
-constexpr int kShStack = LF_SH_STACK;
-constexpr int kOvfEntries = 64 - kShStack;              // the reference's stack holds 64 (closest_hit.glsl:70); deeper scenes are refused at upload
-
-template <bool ANY, bool CULL, bool COUNT>
+// Shared memory of a traversal CTA: the stacks [STACK][128] (16 KB at 32 entries) + the world-space rays [9][128] (4.5 KB).  Measured and
+// rejected in round 2 (profiles/r2/README.md): keeping only 12 stack entries in shared memory with a global overflow array, and
+// re-reading the world ray from the path state instead of parking it here.  Both give the SM's unified array back to the L1 (carve-out
+// 196 KB -> 100 KB, L1 hit rate of the incoherent bounces 26 % -> 35 %), but the walk's bound is the L1 data pipe's wavefront rate, not
+// its capacity: -1 % at best, and the extra live values push the any-hit kernel into spills at its 56-register limit.
+template <bool ANY, bool CULL, bool COUNT, int STACK>
 __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
-                                                       int* cursor, int* __restrict__ overflow, DevCounters* cnt) {
-    __shared__ int stack[kShStack * kBlockThreads];
-    SplitStk<kShStack> stk;
-    stk.col = stack + threadIdx.x;
-    stk.ovfBase = overflow;
-#if LF_WRAY_SHARED
+                                                       int* cursor, DevCounters* cnt) {
+    __shared__ int stack[STACK * kBlockThreads];
     __shared__ float wray[9 * kBlockThreads];           // world-space ray of each lane + 1/direction (restored when a BLAS is left)
+    PlainStk stk;
+    stk.col = stack + threadIdx.x;
     float* wr = wray + threadIdx.x;
-#endif
     const int count = *countp;
     const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
     constexpr unsigned FULL = 0xffffffffu;
@@ -156,29 +144,17 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         maxDist = dd.w;
         return r;
     };
-#if LF_WRAY_SHARED
     auto world_ray = [&]() { Ray r; r.o = mk3(wr[0], wr[kBlockThreads], wr[2 * kBlockThreads]);
                              r.d = mk3(wr[3 * kBlockThreads], wr[4 * kBlockThreads], wr[5 * kBlockThreads]); return r; };
-#else
-    // the world-space ray of this lane, re-read from the path state it was started from (same bits: begin_ray only copied it)
-    auto world_ray = [&]() { Ray r;
-                             if (ANY) { float4 so = A.sh_o[slot]; float4 dd = shPhase == 0 ? A.sh_d0[slot] : A.sh_d1[slot]; r.o = xyz(so); r.d = xyz(dd); }
-                             else { r.o = xyz(A.ray_o[slot]); r.d = xyz(A.ray_d[slot]); }
-                             return r; };
-#endif
     // start the walk of ray r; returns false when the ray is already decided (ANY: an analytic light blocks it)
     auto begin_ray = [&](const Ray& r) -> bool {
-#if LF_WRAY_SHARED
         wr[0] = r.o.x; wr[kBlockThreads] = r.o.y; wr[2 * kBlockThreads] = r.o.z;
         wr[3 * kBlockThreads] = r.d.x; wr[4 * kBlockThreads] = r.d.y; wr[5 * kBlockThreads] = r.d.z;
-#endif
         if (!ANY) hit_clear(hit);
         bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
         if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return false;
         walk_begin(S, r, w, stk);
-#if LF_WRAY_SHARED
         wr[6 * kBlockThreads] = w.idir.x; wr[7 * kBlockThreads] = w.idir.y; wr[8 * kBlockThreads] = w.idir.z;
-#endif
         return true;
     };
 
@@ -232,11 +208,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                     w.inBlas = false;
                     Ray r = world_ray();
                     w.o = r.o; w.d = r.d;
-#if LF_WRAY_SHARED
                     w.idir = mk3(wr[6 * kBlockThreads], wr[7 * kBlockThreads], wr[8 * kBlockThreads]);
-#else
-                    w.idir = mk3(1.0f) / r.d;                // the same quotient walk_begin formed
-#endif
                     w.axis = has_inf(w.idir);
                     w.ref = stk.pop(w.sp);
                 }
@@ -382,6 +354,65 @@ __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P
             }
         }
         queue_push(next, nextCount, alive, s);
+    }
+}
+
+// shade, both parts in one kernel (LF_FUSED_SHADE): the surface record stays in registers between the NEE half and the BSDF-sample
+// half, so the 5 float4 of `State` (sf0..sf4) are never written or re-read, and ray_d / thr / absn / hit_p / rng are read once per
+// bounce instead of twice: about 300 of the 800 bytes of path state a surviving path moves per bounce.
+#ifndef LF_FUSED_MINBLOCKS
+#define LF_FUSED_MINBLOCKS 5
+#endif
+template <bool COUNT, bool ENV, bool LIGHTS, bool TEX>
+__global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
+    const int* queue = Q.active[depth & 1];
+    const int count = Q.counts[0 * Q.stride + depth];
+    int* shadowCount = Q.counts + 1 * Q.stride + depth;
+    int* next = Q.active[(depth + 1) & 1];
+    int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
+    const bool lastBounce = depth + 1 >= P.max_depth;          // the BSDF sample of the last bounce cannot reach the image
+    const int rounded = (count + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool alive = false, wantShadow = false;
+        int s = -1;
+        if (i < count) {
+            s = queue[i];
+            PathRegs ps;
+            float4 o = A.ray_o[s], d = A.ray_d[s], th = A.thr[s], ra = A.rad[s], ab = A.absn[s], st = A.stale[s];
+            uint4 g = A.rng[s];
+            ps.ray.o = xyz(o); ps.ray.d = xyz(d); ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab); ps.stale = xyz(st);
+            ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
+            Hit h;
+            float4 hf = A.hit_f[s]; int4 hi = A.hit_i[s]; float4 hp = A.hit_p[s];
+            h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w; h.fhp = xyz(hp);
+            Nee nee;
+            Surf sf;
+            f3 absnNext;
+            const bool surface = shade_hit<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, sf, absnNext, cnt);
+            wantShadow = nee.has0 || nee.has1;
+            if (wantShadow) {
+                A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
+                if (nee.has0) { A.sh_d0[s] = make_float4(nee.d0.x, nee.d0.y, nee.d0.z, nee.m0); A.sh_c0[s] = make_float4(nee.c0.x, nee.c0.y, nee.c0.z, 0.f); }
+                if (nee.has1) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
+                A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);
+            } else if (surface) {
+                ps.rad = ps.rad + mk3(0.0f) * nee.T;              // radiance += DirectLight() * throughput with Li == 0 (pathtrace.glsl:266)
+            }
+            A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
+            if (surface && !lastBounce) {
+                alive = shade_sample(P, depth, ps, sf, h.fhp, absnNext);
+                if (alive) {
+                    A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
+                    A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+                    A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
+                    A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
+                    A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+                    A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+                }
+            }
+        }
+        queue_push(next, nextCount, alive, s);
+        queue_push(Q.shadow, shadowCount, wantShadow, s);
     }
 }
 
@@ -545,35 +576,20 @@ void launch_node_probe(cudaStream_t stream, const float4* nodes, unsigned num_no
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
-// The kernel's shared memory is static and small; ask for the smallest carve-out that holds the resident CTAs so that the rest of the
-// SM's 256 KB array serves as L1 (the default heuristic may reserve more shared memory than the kernel can ever use).
-template <class K>
-static void prefer_l1(K kernel, int ctas_per_sm) {
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return; }
-    const size_t need = (size_t)ctas_per_sm * (fa.sharedSizeBytes + 1024);           // + the 1 KB the system reserves per CTA
-    int pct = (int)((need * 100 + (size_t)228 * 1024 - 1) / ((size_t)228 * 1024));
-    if (pct > 100) pct = 100;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
-}
-// once per context (function attributes are per device)
-void configure_trace_kernels(int ctas_per_sm) {
-    prefer_l1(k_trace<false, true, false>, ctas_per_sm); prefer_l1(k_trace<true, true, false>, ctas_per_sm);
-    prefer_l1(k_trace<false, false, false>, ctas_per_sm); prefer_l1(k_trace<true, false, false>, ctas_per_sm);
-    prefer_l1(k_trace<false, true, true>, ctas_per_sm); prefer_l1(k_trace<true, true, true>, ctas_per_sm);
-    prefer_l1(k_trace<false, false, true>, ctas_per_sm); prefer_l1(k_trace<true, false, true>, ctas_per_sm);
-}
 template <bool CULL, bool COUNT>
 static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
-    if (which == 0) k_trace<false, CULL, COUNT><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.stack_overflow, L.counters);
-    else k_trace<true, CULL, COUNT><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.stack_overflow, L.counters);
+    if (L.stack_depth <= 32) {
+        if (which == 0) k_trace<false, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+        else k_trace<true, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+    } else {
+        if (which == 0) k_trace<false, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+        else k_trace<true, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+    }
 }
 static void launch_trace(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
     if (L.cull) { if (L.count) launch_trace_kernels_s<true, true>(L, which, queue, countp, cursor); else launch_trace_kernels_s<true, false>(L, which, queue, countp, cursor); }
     else { if (L.count) launch_trace_kernels_s<false, true>(L, which, queue, countp, cursor); else launch_trace_kernels_s<false, false>(L, which, queue, countp, cursor); }
 }
-
-int trace_overflow_entries() { return kOvfEntries; }
 
 void launch_generate(const LaunchCtx& L) {
     int total = L.params.num_frames * L.params.slots_per_frame;
@@ -644,13 +660,26 @@ void launch_extend(const LaunchCtx& L, int depth) {
     if (L.sort && (L.sort->mode & 1) && depth >= 1) queue = sort_queue<false>(L, queue, countp);   // primary rays are coherent already (8x4 pixel blocks per warp)
     launch_trace(L, 0, queue, countp, Q.counts + 2 * Q.stride + depth);
 }
+#ifndef LF_FUSED_SHADE
+#define LF_FUSED_SHADE 0
+#endif
+bool shade_is_fused() { return LF_FUSED_SHADE != 0; }
 template <bool ENV, bool LIGHTS, bool TEX>
 static void launch_shade_v(const LaunchCtx& L, int depth, int blocks) {
+#if LF_FUSED_SHADE
+    k_shade_fused<false, ENV, LIGHTS, TEX><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+#else
     k_shade<false, ENV, LIGHTS, TEX><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+#endif
 }
 void launch_shade(const LaunchCtx& L, int depth) {
+#if LF_FUSED_SHADE
+    int blocks = L.sm_count * LF_FUSED_MINBLOCKS;
+    if (L.count) { k_shade_fused<true, true, true, true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters); return; }
+#else
     int blocks = L.sm_count * LF_SHADE_MINBLOCKS;      // exactly one resident wave (more CTAs than fit measured 25 % slower)
     if (L.count) { k_shade<true, true, true, true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters); return; }
+#endif
     const bool env = L.params.use_envmap != 0, lights = L.scene.num_lights > 0, tex = L.scene.num_tex > 0;
     switch ((env ? 4 : 0) | (lights ? 2 : 0) | (tex ? 1 : 0)) {
         case 0: launch_shade_v<false, false, false>(L, depth, blocks); break;
@@ -664,6 +693,7 @@ void launch_shade(const LaunchCtx& L, int depth) {
     }
 }
 void launch_sample(const LaunchCtx& L, int depth) {
+    if (shade_is_fused()) return;                      // the BSDF sample ran inside the shade kernel
     k_sample<<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
 }
 void launch_shadow(const LaunchCtx& L, int depth) {

@@ -30,15 +30,13 @@ struct LaunchCtx {
     int stack_depth;         // traversal stack entries the scene needs (<= 64)
     bool cull, count;
     const SortCtx* sort = nullptr;   // non-null = sort the extend queue of bounces >= 1
-    int* stack_overflow = nullptr;   // traversal stack entries beyond the shared-memory part: [trace_overflow_entries()][persistent threads]
 };
-int trace_overflow_entries();
-void configure_trace_kernels(int ctas_per_sm);   // shared-memory carve-out of the traversal kernels on the current device
 
 void launch_generate(const LaunchCtx& L);
 void launch_extend(const LaunchCtx& L, int depth);
 void launch_shade(const LaunchCtx& L, int depth);
 void launch_sample(const LaunchCtx& L, int depth);
+bool shade_is_fused();   // LF_FUSED_SHADE: launch_shade runs both halves, launch_sample is a no-op
 void launch_shadow(const LaunchCtx& L, int depth);
 void launch_accumulate(const LaunchCtx& L, float* accum);
 void launch_preview_store(const LaunchCtx& L, float* preview);

@@ -84,7 +84,6 @@ struct lfcuda_ctx {
     float* d_preview = nullptr; float* d_preview_out = nullptr;   // preview engine target (pathTraceTextureLowRes) + its post-processed copy
     size_t preview_cap = 0; int preview_w = 0, preview_h = 0;
     DevCounters* d_counters = nullptr;
-    int* d_stack_overflow = nullptr;      // traversal stack entries beyond the shared-memory part, [trace_overflow_entries()][persistent threads]
 
     // instrumentation
     bool profiling = false;
@@ -326,9 +325,9 @@ int check_ready(lfcuda_ctx* ctx) {
 void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
     L.scene = c->dev; L.params = D; L.soa = c->soa; L.queues = c->queues; L.counters = c->d_counters; L.stream = c->stream;
     L.sm_count = c->prop.multiProcessorCount;
-    L.persistent_blocks = L.sm_count * c->ctas_per_sm;
+    // the 64-entry stack variant needs 38.4 KB of shared memory per CTA: 5 CTAs per SM are resident, not 9
+    L.persistent_blocks = L.sm_count * (c->packed.stack_depth > 32 ? std::min(c->ctas_per_sm, 5) : c->ctas_per_sm);
     L.stack_depth = c->packed.stack_depth;
-    L.stack_overflow = c->d_stack_overflow;
     L.cull = !c->params.no_cull;
     L.count = c->params.count_work != 0;
     L.sort = (c->sort_rays && c->sort.sorted) ? &c->sort : nullptr;
@@ -424,17 +423,6 @@ int lfcuda_create(lfcuda_ctx** out, int device) {
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("LF_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 16) c->ctas_per_sm = v; }
-    {
-        const size_t threads = (size_t)c->prop.multiProcessorCount * c->ctas_per_sm * kBlockThreads;
-        cudaError_t e3 = cudaMalloc((void**)&c->d_stack_overflow, std::max<size_t>(1, (size_t)trace_overflow_entries()) * threads * sizeof(int));
-        if (e3 != cudaSuccess) {
-            fail(nullptr, LFCUDA_ENOMEM, "traversal stack overflow array: %s", cudaGetErrorString(e3));
-            cudaFree(c->d_counters); cudaStreamDestroy(c->own_stream);
-            delete c;
-            return LFCUDA_ENOMEM;
-        }
-        configure_trace_kernels(c->ctas_per_sm);
-    }
     if (const char* e = getenv("LF_SORT_RAYS")) { c->sort.mode = atoi(e) & 3; c->sort_rays = c->sort.mode != 0; }
     *out = c;
     return 0;
@@ -451,7 +439,6 @@ void lfcuda_destroy(lfcuda_ctx* c) {
     free_frame(c);
     if (c->queues.counts) cudaFree(c->queues.counts);
     cudaFree(c->d_counters);
-    cudaFree(c->d_stack_overflow);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -263,9 +263,10 @@ def test_multi_gpu_renderer_behind_the_single_construction(cornell_scene, golden
         np.testing.assert_allclose(img, single, rtol=2e-5, atol=1e-6)
         u8 = r.GetOutputBuffer()
         np.testing.assert_array_equal(u8, np.rint(np.clip(img, 0, 1) * 255).astype(np.uint8))
-        # progressive: more samples after a read-out, then a camera move resets every device
+        # progressive: more samples after a read-out (the same call sequence on one GPU: a loop that is re-entered after its auto-stop
+        # has already Update()d once, Main.cpp:197-206), then a camera move resets every device
         r.Run(n + 8)
-        r1 = lf.CudaRenderer(cornell_scene); r1.Run(n + 8)
+        r1 = lf.CudaRenderer(cornell_scene); r1.Run(n); r1.GetOutputBufferHDR(); r1.Run(n + 8)
         np.testing.assert_allclose(r.GetOutputBufferHDR(), r1.GetOutputBufferHDR(), rtol=2e-5, atol=1e-6)
         r1.close()
         cornell_scene.set_camera_moving(True)
