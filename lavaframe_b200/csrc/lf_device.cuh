@@ -266,7 +266,9 @@ LFD void to_instance(const float4 r0, const float4 r1, const float4 r2, const Ra
 
 // One step of the walk for a reference that is not a triangle leaf: inner node, instance entry, or stack marker.
 // Returns false when the walk is over (marker popped at world level).  `limit` = current best t (closest) or maxDist (any).
-template <bool ANY, bool CULL, bool COUNT, class ST>
+// AXM: how the slab test treats Walk::axis.  0 = look at the flag (per-thread walks), 1 = the caller guarantees !w.axis (k_trace's
+// inner loop: no branch per node), 2 = the caller guarantees w.axis (k_trace steps those rare lanes apart, one node at a time).
+template <bool ANY, bool CULL, bool COUNT, int AXM = 0, class ST>
 LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, const ST& stk, DevCounters* cnt) {
     if (w.ref >= 0) {                             // inner node (closest_hit.glsl:167-199)
         bump<COUNT>(cnt, C_INNER); if (ANY) bump<COUNT>(cnt, C_INNER_SH);
@@ -285,8 +287,9 @@ LFD bool walk_step(const DevScene& S, const Ray& r, Walk& w, float limit, const 
         float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2), n3 = ldg4(n + 3);
 #endif
         float le, re;
-        float leftHit = AABBIntersect(mk3(n0.x, n0.y, n0.z), mk3(n0.w, n1.x, n1.y), w.o, w.idir, w.axis, le);
-        float rightHit = AABBIntersect(mk3(n1.z, n1.w, n2.x), mk3(n2.y, n2.z, n2.w), w.o, w.idir, w.axis, re);
+        const bool axisRay = AXM == 0 ? w.axis : AXM == 2;
+        float leftHit = AABBIntersect(mk3(n0.x, n0.y, n0.z), mk3(n0.w, n1.x, n1.y), w.o, w.idir, axisRay, le);
+        float rightHit = AABBIntersect(mk3(n1.z, n1.w, n2.x), mk3(n2.y, n2.z, n2.w), w.o, w.idir, axisRay, re);
         int leftRef = __float_as_int(n3.x), rightRef = __float_as_int(n3.y);
         bool lok = leftHit > 0.0f, rok = rightHit > 0.0f;
         if (CULL) {

@@ -192,14 +192,22 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         bool rayDone = false;
         const int liveLanes = __popc(__ballot_sync(FULL, alive));
         for (;;) {
-            const bool canStep = alive && w.ref >= 0;
+            const bool canStep = alive && w.ref >= 0 && !w.axis;
             const unsigned stepMask = __ballot_sync(FULL, canStep);
             if (stepMask == 0u || (liveLanes - __popc(stepMask)) * kLeafGather >= liveLanes) break;
             if (canStep) {
                 Ray r;                                       // not read by an inner-node step
-                walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+                walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
             }
         }
+        // ---- phase 1x: lanes whose ray is parallel to an axis (1 / d infinite: the slab test takes its NaN-exact form, lf_device.cuh
+        // AABBIntersect) park at inner nodes too and take ONE step here per round.  Such rays are vanishingly rare outside hand-built
+        // tests, and keeping them out of the loop above keeps that loop free of the test.
+        if (alive && w.ref >= 0 && w.axis) {
+            Ray r;
+            walk_step<ANY, CULL, COUNT, 2>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+        }
+        __syncwarp();
         // ---- phase 2a: instance entries / exits of the parked lanes, together
         if (alive && w.ref < 0 && (w.ref & kRefTlasBit)) {
             if (w.ref == kRefSentinel) {
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                 }
             } else {
                 Ray r = world_ray();
-                walk_step<ANY, CULL, COUNT>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+                walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);   // an instance entry (the inner-node branch is not taken)
             }
         }
         __syncwarp();
@@ -254,14 +262,15 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
 
 // ---------------------------------------------------------------------------------------------- shade
 #ifndef LF_SHADE_MINBLOCKS
-#define LF_SHADE_MINBLOCKS 7   // 72 registers.  ms of k_shade per 6 C2 steps with the llvmpipe-exact math: 6: 83.7, 7: 84.9, 8: 93.9, 9: 97.3, 10: 107.7
-                               // (profiles/r1_experiments/ab_shade_sample_ctas.txt); with the Cephes math of the earlier round 8 was best (4: 137, 8: 113, 10: 123 per 8 steps)
+#define LF_SHADE_MINBLOCKS 5   // 96 registers.  ms of k_shade per 6 steps, C2 / C4: 5 CTAs per SM: 77.9 / 440, 6: 82.8 / 479, 7: 83.8 / 529 (profiles/r2/r2a_ab_*;
+                               // round 1: 8: 93.9, 9: 97.3, 10: 107.7 on C2, profiles/r1_experiments/ab_shade_sample_ctas.txt): the kernel is latency-bound
+                               // and wants registers (no spill traffic on top of its scattered loads), not warps
 #endif
 // shade, part A: hit processing + next-event estimation.  Surface hits that go on are appended to the sample queue with
 // the part of `State` DisneySample needs (5 float4 per path).
 template <bool COUNT, bool ENV, bool LIGHTS, bool TEX>
 __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
-    const int* queue = Q.active[depth & 1];
+    const int* queue = (depth & 1) ? Q.active[1] : Q.active[0];   // (a select, not an index: indexing would copy the parameter struct to local memory)
     const int count = Q.counts[0 * Q.stride + depth];
     int* sampleCount = Q.counts + 4 * Q.stride + depth;
     int* shadowCount = Q.counts + 1 * Q.stride + depth;
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
 #endif
 __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
     const int count = Q.counts[4 * Q.stride + depth];
-    int* next = Q.active[(depth + 1) & 1];
+    int* next = (depth & 1) ? Q.active[0] : Q.active[1];
     int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
     const int rounded = (count + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
@@ -357,18 +366,22 @@ __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P
     }
 }
 
-// shade, both parts in one kernel (LF_FUSED_SHADE): the surface record stays in registers between the NEE half and the BSDF-sample
-// half, so the 5 float4 of `State` (sf0..sf4) are never written or re-read, and ray_d / thr / absn / hit_p / rng are read once per
-// bounce instead of twice: about 300 of the 800 bytes of path state a surviving path moves per bounce.
+// shade, both parts in one kernel: the surface record stays in registers between the NEE half and the BSDF-sample half, so the 5
+// float4 of `State` (sf0..sf4) are never written or re-read, and ray_d / thr / absn / hit_p / rng are read once per bounce instead of
+// twice: about 300 of the 800 bytes of path state a surviving path moves per bounce.  What it gives up is the compaction between
+// the halves: lanes whose path ended in part A (miss, emitter) idle through DisneySample.  Measured (profiles/r2/r2c_ab_*, shade +
+// sample ms per 6 steps, split -> fused at 4 CTAs per SM): closed scenes win, C1 7.26 -> 4.28, C4 806 -> 742; scenes whose rays escape
+// lose, C2 (env map, half of the bounce-0 rays see the sky) 114 -> 146, C3 (open, textured) 140 -> 215.  launch_shade therefore fuses
+// only the variants without an environment map and without textures (LF_FUSED_SHADE: 0 never, 1 that rule, 2 always).
 #ifndef LF_FUSED_MINBLOCKS
-#define LF_FUSED_MINBLOCKS 5
+#define LF_FUSED_MINBLOCKS 4
 #endif
 template <bool COUNT, bool ENV, bool LIGHTS, bool TEX>
 __global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
-    const int* queue = Q.active[depth & 1];
+    const int* queue = (depth & 1) ? Q.active[1] : Q.active[0];   // (a select, not an index: indexing would copy the parameter struct to local memory)
     const int count = Q.counts[0 * Q.stride + depth];
     int* shadowCount = Q.counts + 1 * Q.stride + depth;
-    int* next = Q.active[(depth + 1) & 1];
+    int* next = (depth & 1) ? Q.active[0] : Q.active[1];
     int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
     const bool lastBounce = depth + 1 >= P.max_depth;          // the BSDF sample of the last bounce cannot reach the image
     const int rounded = (count + 31) & ~31;
@@ -661,39 +674,37 @@ void launch_extend(const LaunchCtx& L, int depth) {
     launch_trace(L, 0, queue, countp, Q.counts + 2 * Q.stride + depth);
 }
 #ifndef LF_FUSED_SHADE
-#define LF_FUSED_SHADE 0
+#define LF_FUSED_SHADE 1
 #endif
-bool shade_is_fused() { return LF_FUSED_SHADE != 0; }
+// does launch_shade run both halves in one kernel for this scene?  (then launch_sample is a no-op)
+bool shade_is_fused(const LaunchCtx& L) {
+    if (LF_FUSED_SHADE == 2) return true;
+    if (LF_FUSED_SHADE == 0 || L.count) return false;
+    return L.params.use_envmap == 0 && L.scene.num_tex == 0;
+}
 template <bool ENV, bool LIGHTS, bool TEX>
-static void launch_shade_v(const LaunchCtx& L, int depth, int blocks) {
-#if LF_FUSED_SHADE
-    k_shade_fused<false, ENV, LIGHTS, TEX><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
-#else
-    k_shade<false, ENV, LIGHTS, TEX><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
-#endif
+static void launch_shade_v(const LaunchCtx& L, int depth, bool fused) {
+    if (fused) k_shade_fused<false, ENV, LIGHTS, TEX><<<L.sm_count * LF_FUSED_MINBLOCKS, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+    else k_shade<false, ENV, LIGHTS, TEX><<<L.sm_count * LF_SHADE_MINBLOCKS, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
 }
 void launch_shade(const LaunchCtx& L, int depth) {
-#if LF_FUSED_SHADE
-    int blocks = L.sm_count * LF_FUSED_MINBLOCKS;
-    if (L.count) { k_shade_fused<true, true, true, true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters); return; }
-#else
-    int blocks = L.sm_count * LF_SHADE_MINBLOCKS;      // exactly one resident wave (more CTAs than fit measured 25 % slower)
-    if (L.count) { k_shade<true, true, true, true><<<blocks, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters); return; }
-#endif
+    // grids are exactly one resident wave (more CTAs than fit measured 25 % slower)
+    if (L.count) { k_shade<true, true, true, true><<<L.sm_count * LF_SHADE_MINBLOCKS, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters); return; }
     const bool env = L.params.use_envmap != 0, lights = L.scene.num_lights > 0, tex = L.scene.num_tex > 0;
+    const bool fused = shade_is_fused(L);
     switch ((env ? 4 : 0) | (lights ? 2 : 0) | (tex ? 1 : 0)) {
-        case 0: launch_shade_v<false, false, false>(L, depth, blocks); break;
-        case 1: launch_shade_v<false, false, true>(L, depth, blocks); break;
-        case 2: launch_shade_v<false, true, false>(L, depth, blocks); break;
-        case 3: launch_shade_v<false, true, true>(L, depth, blocks); break;
-        case 4: launch_shade_v<true, false, false>(L, depth, blocks); break;
-        case 5: launch_shade_v<true, false, true>(L, depth, blocks); break;
-        case 6: launch_shade_v<true, true, false>(L, depth, blocks); break;
-        default: launch_shade_v<true, true, true>(L, depth, blocks); break;
+        case 0: launch_shade_v<false, false, false>(L, depth, fused); break;
+        case 1: launch_shade_v<false, false, true>(L, depth, fused); break;
+        case 2: launch_shade_v<false, true, false>(L, depth, fused); break;
+        case 3: launch_shade_v<false, true, true>(L, depth, fused); break;
+        case 4: launch_shade_v<true, false, false>(L, depth, fused); break;
+        case 5: launch_shade_v<true, false, true>(L, depth, fused); break;
+        case 6: launch_shade_v<true, true, false>(L, depth, fused); break;
+        default: launch_shade_v<true, true, true>(L, depth, fused); break;
     }
 }
 void launch_sample(const LaunchCtx& L, int depth) {
-    if (shade_is_fused()) return;                      // the BSDF sample ran inside the shade kernel
+    if (shade_is_fused(L)) return;                     // the BSDF sample ran inside the shade kernel
     k_sample<<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
 }
 void launch_shadow(const LaunchCtx& L, int depth) {

@@ -36,7 +36,7 @@ void launch_generate(const LaunchCtx& L);
 void launch_extend(const LaunchCtx& L, int depth);
 void launch_shade(const LaunchCtx& L, int depth);
 void launch_sample(const LaunchCtx& L, int depth);
-bool shade_is_fused();   // LF_FUSED_SHADE: launch_shade runs both halves, launch_sample is a no-op
+bool shade_is_fused(const LaunchCtx& L);   // launch_shade runs both halves in one kernel, launch_sample is a no-op
 void launch_shadow(const LaunchCtx& L, int depth);
 void launch_accumulate(const LaunchCtx& L, float* accum);
 void launch_preview_store(const LaunchCtx& L, float* preview);
