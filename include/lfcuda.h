@@ -167,6 +167,16 @@ int  lfcuda_update_instances(lfcuda_ctx* ctx, const float* transforms, int32_t n
                              const float* materials, int32_t num_materials,
                              const float* tlas_nodes, int32_t first_node, int32_t num_tlas_nodes);
 
+/* The same update with the TLAS REBUILT ON THE DEVICE from the instance matrices (csrc/lf_tlas.cu): what Scene::RebuildInstances does on the
+ * host (createTLAS, Scene.cpp:106-146; Bvh::Build without SAH, thirdparty/RadeonRays/bvh.cpp:40-243; BvhTranslator::UpdateTLAS,
+ * bvh_translator.cpp:61-89,134-140), node for node, plus the instance records.  Only the matrices (and materials) are uploaded.
+ * instance_material_ids: NULL, or the materialID of every instance if those changed.  On LFCUDA_ELIMIT the scene must be uploaded again. */
+int  lfcuda_update_instances_device(lfcuda_ctx* ctx, const float* transforms, int32_t num_instances,
+                                    const float* materials, int32_t num_materials, const int32_t* instance_material_ids);
+/* Parity probe: the TLAS nodes the device holds, in the reference's layout (9 floats per node, 2 * num_instances - 1 nodes in the
+ * order of bvhTranslator.nodes from topLevelIndex on). */
+int  lfcuda_read_tlas_nodes(lfcuda_ctx* ctx, float* nodes_out, int32_t max_nodes, int32_t* num_nodes_out);
+
 /* ---- per-frame uniforms (TiledRenderer::Init :222-227, ::Update :505-521) ----------------------- */
 int  lfcuda_set_params(lfcuda_ctx* ctx, const LfParams* params);
 int  lfcuda_set_camera(lfcuda_ctx* ctx, const LfCamera* camera);
@@ -235,6 +245,8 @@ int  lfcuda_group_upload_scene(lfcuda_group* g, const LfSceneView* scene);      
 int  lfcuda_group_update_instances(lfcuda_group* g, const float* transforms, int32_t num_instances,
                                    const float* materials, int32_t num_materials,
                                    const float* tlas_nodes, int32_t first_node, int32_t num_tlas_nodes);
+int  lfcuda_group_update_instances_device(lfcuda_group* g, const float* transforms, int32_t num_instances,
+                                          const float* materials, int32_t num_materials, const int32_t* instance_material_ids);
 int  lfcuda_group_set_params(lfcuda_group* g, const LfParams* params);
 int  lfcuda_group_set_camera(lfcuda_group* g, const LfCamera* camera);
 int  lfcuda_group_set_post(lfcuda_group* g, const LfPostParams* post);

@@ -81,6 +81,8 @@ LFCUDA_SYMBOLS = {
     "lfcuda_synchronize": (C.c_int, [C.c_void_p]),
     "lfcuda_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(LfSceneView)]),
     "lfcuda_update_instances": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32]),
+    "lfcuda_update_instances_device": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "lfcuda_read_tlas_nodes": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.POINTER(C.c_int32)]),
     "lfcuda_set_params": (C.c_int, [C.c_void_p, C.POINTER(LfParams)]),
     "lfcuda_set_camera": (C.c_int, [C.c_void_p, C.POINTER(LfCamera)]),
     "lfcuda_set_post": (C.c_int, [C.c_void_p, C.POINTER(LfPostParams)]),
@@ -94,6 +96,7 @@ LFCUDA_SYMBOLS = {
     "lfcuda_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "lfcuda_group_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(LfSceneView)]),
     "lfcuda_group_update_instances": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32]),
+    "lfcuda_group_update_instances_device": (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, C.POINTER(C.c_int32)]),
     "lfcuda_group_set_params": (C.c_int, [C.c_void_p, C.POINTER(LfParams)]),
     "lfcuda_group_set_camera": (C.c_int, [C.c_void_p, C.POINTER(LfCamera)]),
     "lfcuda_group_set_post": (C.c_int, [C.c_void_p, C.POINTER(LfPostParams)]),

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
 
 // shade, part B: BSDF sample, throughput, Russian roulette, next ray; survivors are appended to the next bounce's queue.
 #ifndef LF_SAMPLE_MINBLOCKS
-#define LF_SAMPLE_MINBLOCKS 8
+#define LF_SAMPLE_MINBLOCKS 6   // ms of k_sample per 6 C2 steps: 6 CTAs per SM 26.3, 8: 30.4 (profiles/r2/r2d_ab_c2_full_shade4s6.json)
 #endif
 __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
     const int count = Q.counts[4 * Q.stride + depth];
@@ -371,8 +371,11 @@ __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P
 // twice: about 300 of the 800 bytes of path state a surviving path moves per bounce.  What it gives up is the compaction between
 // the halves: lanes whose path ended in part A (miss, emitter) idle through DisneySample.  Measured (profiles/r2/r2c_ab_*, shade +
 // sample ms per 6 steps, split -> fused at 4 CTAs per SM): closed scenes win, C1 7.26 -> 4.28, C4 806 -> 742; scenes whose rays escape
-// lose, C2 (env map, half of the bounce-0 rays see the sky) 114 -> 146, C3 (open, textured) 140 -> 215.  launch_shade therefore fuses
-// only the variants without an environment map and without textures (LF_FUSED_SHADE: 0 never, 1 that rule, 2 always).
+// lose, C2 (env map, half of the bounce-0 rays see the sky) 114 -> 146, C3 (open, textured) 140 -> 215.  With k_shade at 5 CTAs per SM
+// the split pair then overtook the fused kernel on C4 as well (697 against 747, profiles/r2/r2d_ab_c4_stress_nofuse.json), while C1's
+// 2 M-path batches, where a launch per bounce and its tail are what is saved, keep the gain (831 -> 981 M samples/s).  launch_shade
+// therefore fuses only small batches (<= 4 M path slots) of scenes without an environment map and without textures
+// (LF_FUSED_SHADE: 0 never, 1 that rule, 2 always).
 #ifndef LF_FUSED_MINBLOCKS
 #define LF_FUSED_MINBLOCKS 4
 #endif
@@ -680,7 +683,7 @@ void launch_extend(const LaunchCtx& L, int depth) {
 bool shade_is_fused(const LaunchCtx& L) {
     if (LF_FUSED_SHADE == 2) return true;
     if (LF_FUSED_SHADE == 0 || L.count) return false;
-    return L.params.use_envmap == 0 && L.scene.num_tex == 0;
+    return L.params.use_envmap == 0 && L.scene.num_tex == 0 && (long long)L.params.num_frames * L.params.slots_per_frame <= (4ll << 20);
 }
 template <bool ENV, bool LIGHTS, bool TEX>
 static void launch_shade_v(const LaunchCtx& L, int depth, bool fused) {

@@ -44,6 +44,25 @@ void launch_megakernel(const LaunchCtx& L);
 void launch_export_hits(const LaunchCtx& L, float* t, int* tri, int* mat, int* emitter);
 void launch_node_probe(cudaStream_t stream, const float4* nodes, unsigned num_nodes_pow2, int steps, unsigned* sink, int blocks);
 void launch_read_probe(cudaStream_t stream, const float4* buf, size_t n4, int passes, float* sink, int blocks);
+// Device-side TLAS rebuild (lf_tlas.cu).  All pointers are device memory.
+struct TlasBuild {
+    const float*  transforms;     // n x 16, the reference's Mat4 layout
+    const float*  blas_box;       // n x 6: pmin, pmax of the instance's mesh BVH (the box of its BLAS root node)
+    const int*    inst_blas_root; // n: flat node index of the instance's BLAS root (TLAS leaf LRLeaf.x)
+    const int*    inst_blas_ref;  // n: the same as a packed child reference (lf_types.h)
+    const int*    inst_mat;       // n: materialID (TLAS leaf LRLeaf.y)
+    int n, top_index, inner_base; // instances; first flat TLAS node; packed index of the first TLAS inner node
+    float*  flat_tlas;            // out: (2n - 1) x 9 floats, the reference's node layout, pre-order from top_index
+    float4* packed_nodes;         // out: base of the packed inner-node array (the TLAS part is rewritten)
+    float4* inst_records;         // out: kInstStride float4 per instance
+    int*    result;               // out: [0] top reference, [1] inner nodes on the longest root-to-leaf chain
+    float *bmin, *bmax, *cent;    // scratch: n x 3 each
+    int*   prim;                  // scratch: n
+    void  *queue0, *queue1;       // scratch: n requests each (tlas_request_bytes())
+};
+size_t tlas_request_bytes();
+void launch_tlas_build(cudaStream_t stream, const TlasBuild& T, int sm_count);
+
 constexpr int kMaxGroupDevices = 16;
 void launch_post_sum(cudaStream_t stream, const float* const* accums, int naccum, float* out_f, unsigned char* out_u8, float* sum_out, int W, int H,
                      float inv, int tonemap, const LfPostParams& pp);

@@ -18,6 +18,8 @@ struct PackedScene {
     int top_ref = 0;
     int stack_depth = 0;            // stack entries a traversal can need
     int num_inner = 0;
+    int max_blas_height = 0;        // inner nodes on the longest chain of any instanced BLAS (stack_depth = 2 + TLAS height + this + 1)
+    int num_blas_inner = 0;         // inner nodes below top_bvh_index: the packed index of the first TLAS inner node
 };
 
 // Returns false and fills `err` when the arrays are inconsistent or exceed a structural limit.

@@ -63,6 +63,13 @@ struct lfcuda_ctx {
     float4* d_nodes = nullptr; size_t nodes_cap = 0;
     float4* d_inst = nullptr;
     float4* d_materials = nullptr; int materials_cap = 0;
+    // device-side TLAS rebuild (lf_tlas.cu): per-instance constants taken from the uploaded TLAS leaves, outputs and scratch
+    float* d_transforms = nullptr; float* d_blas_box = nullptr;
+    int *d_inst_blas_root = nullptr, *d_inst_blas_ref = nullptr, *d_inst_mat = nullptr;
+    float* d_flat_tlas = nullptr; int* d_tlas_result = nullptr;
+    float *d_tlas_bmin = nullptr, *d_tlas_bmax = nullptr, *d_tlas_cent = nullptr; int* d_tlas_prim = nullptr;
+    void *d_tlas_q0 = nullptr, *d_tlas_q1 = nullptr;
+    bool tlas_ready = false;
 
     // uniforms
     bool have_params = false, have_camera = false;
@@ -139,6 +146,7 @@ void free_scene(lfcuda_ctx* c) {
     c->tex_array = c->hdr_array = nullptr;
     c->dev = DevScene{};
     c->have_scene = false;
+    c->tlas_ready = false;
 }
 
 // Device memory of a context comes in three independent groups, so that changing one render parameter never disturbs what
@@ -522,6 +530,45 @@ static int upload_scene_impl(lfcuda_ctx* ctx, const LfSceneView* v) {
             ctx->sort.inv[k] = hi > lo ? (float)(1 << kSortCellBits) / (hi - lo) : 0.f;
         }
     }
+    {   // what the device-side TLAS rebuild needs per instance: BLAS root (flat index, packed reference, box) and materialID, from the TLAS leaves
+        const int ni = v->num_instances;
+        std::vector<int> root(ni, 0), ref(ni, 0), mat(ni, 0);
+        std::vector<float> box((size_t)6 * ni, 0.f);
+        for (int i = v->top_bvh_index; i < v->num_nodes; i++) {
+            const float* nd = v->bvh_nodes + 9 * (size_t)i;
+            const int leaf = (int)nd[8];
+            if (leaf >= 0) continue;
+            const int inst = -leaf - 1;
+            if (inst < 0 || inst >= ni) continue;
+            root[inst] = (int)nd[6]; mat[inst] = (int)nd[7];
+            std::memcpy(&ref[inst], &P.inst[(size_t)kInstStride * inst + 3].x, 4);
+            std::memcpy(&box[(size_t)6 * inst], v->bvh_nodes + 9 * (size_t)root[inst], 6 * sizeof(float));
+        }
+        float* dbox; int *droot, *dref, *dmat;
+        if ((r = upload(ctx, box.data(), box.size(), &dbox, ctx->scene_allocs))) return r;
+        if ((r = upload(ctx, root.data(), root.size(), &droot, ctx->scene_allocs))) return r;
+        if ((r = upload(ctx, ref.data(), ref.size(), &dref, ctx->scene_allocs))) return r;
+        if ((r = upload(ctx, mat.data(), mat.size(), &dmat, ctx->scene_allocs))) return r;
+        CK(cudaStreamSynchronize(ctx->stream));             // the vectors above go out of scope
+        ctx->d_blas_box = dbox; ctx->d_inst_blas_root = droot; ctx->d_inst_blas_ref = dref; ctx->d_inst_mat = dmat;
+        auto S = [&](void** p, size_t bytes) -> int {
+            CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+            ctx->scene_allocs.push_back(*p);
+            return 0;
+        };
+        if ((r = S((void**)&ctx->d_transforms, (size_t)16 * ni * sizeof(float)))) return r;
+        if ((r = S((void**)&ctx->d_flat_tlas, (size_t)9 * (2 * ni) * sizeof(float)))) return r;
+        if ((r = S((void**)&ctx->d_tlas_result, 4 * sizeof(int)))) return r;
+        if ((r = S((void**)&ctx->d_tlas_bmin, (size_t)3 * ni * sizeof(float)))) return r;
+        if ((r = S((void**)&ctx->d_tlas_bmax, (size_t)3 * ni * sizeof(float)))) return r;
+        if ((r = S((void**)&ctx->d_tlas_cent, (size_t)3 * ni * sizeof(float)))) return r;
+        if ((r = S((void**)&ctx->d_tlas_prim, (size_t)ni * sizeof(int)))) return r;
+        if ((r = S(&ctx->d_tlas_q0, (size_t)ni * tlas_request_bytes()))) return r;
+        if ((r = S(&ctx->d_tlas_q1, (size_t)ni * tlas_request_bytes()))) return r;
+        CK(cudaMemcpyAsync(ctx->d_flat_tlas, v->bvh_nodes + 9 * (size_t)v->top_bvh_index,
+                           (size_t)9 * std::min(2 * ni, v->num_nodes - v->top_bvh_index) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->tlas_ready = true;
+    }
     D.top_ref = P.top_ref;
     D.num_lights = v->num_lights; D.num_materials = v->num_materials; D.num_instances = v->num_instances;
 
@@ -595,7 +642,59 @@ int lfcuda_update_instances(lfcuda_ctx* ctx, const float* transforms, int32_t nu
         ctx->dev.num_materials = num_materials;
     }
     ctx->dev.top_ref = ctx->packed.top_ref;
+    if (ctx->tlas_ready)   // the device's copy of the flat TLAS follows (lfcuda_read_tlas_nodes)
+        CK(cudaMemcpyAsync(ctx->d_flat_tlas, tlas_nodes, (size_t)9 * std::min(num_tlas_nodes, 2 * num_instances) * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// The same update with the TLAS rebuilt on the device (lf_tlas.cu): only the matrices (and the materials) cross the bus.
+int lfcuda_update_instances_device(lfcuda_ctx* ctx, const float* transforms, int32_t num_instances, const float* materials, int32_t num_materials,
+                                   const int32_t* instance_material_ids) {
+    if (!ctx || !ctx->have_scene || !ctx->tlas_ready) return fail(ctx, LFCUDA_EINVAL, "no scene uploaded");
+    if (!transforms || num_instances != ctx->dev.num_instances) return fail(ctx, LFCUDA_EINVAL, "instance count changed (%d != %d)", num_instances, ctx->dev.num_instances);
+    if (materials && num_materials > ctx->materials_cap) return fail(ctx, LFCUDA_EINVAL, "material count grew (%d > %d)", num_materials, ctx->materials_cap);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int n = num_instances;
+    CK(cudaMemcpyAsync(ctx->d_transforms, transforms, (size_t)16 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (instance_material_ids) CK(cudaMemcpyAsync(ctx->d_inst_mat, instance_material_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (materials) {
+        CK(cudaMemcpyAsync(ctx->d_materials, materials, (size_t)28 * num_materials * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->dev.num_materials = num_materials;
+    }
+    TlasBuild T{};
+    T.transforms = ctx->d_transforms; T.blas_box = ctx->d_blas_box; T.inst_blas_root = ctx->d_inst_blas_root; T.inst_blas_ref = ctx->d_inst_blas_ref;
+    T.inst_mat = ctx->d_inst_mat; T.n = n; T.top_index = ctx->top_index; T.inner_base = ctx->packed.num_blas_inner;
+    T.flat_tlas = ctx->d_flat_tlas; T.packed_nodes = ctx->d_nodes; T.inst_records = ctx->d_inst; T.result = ctx->d_tlas_result;
+    T.bmin = ctx->d_tlas_bmin; T.bmax = ctx->d_tlas_bmax; T.cent = ctx->d_tlas_cent; T.prim = ctx->d_tlas_prim;
+    T.queue0 = ctx->d_tlas_q0; T.queue1 = ctx->d_tlas_q1;
+    ctx->launches += 3;
+    launch_tlas_build(ctx->stream, T, ctx->prop.multiProcessorCount);
+    CK(cudaGetLastError());
+    int res[2] = {0, 0};
+    CK(cudaMemcpyAsync(res, ctx->d_tlas_result, sizeof res, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int depth = 2 + res[1] + ctx->packed.max_blas_height + 1;
+    if (depth > 64) {
+        ctx->have_scene = false;   // the device TLAS now describes a scene the 64-entry stack cannot walk: refuse to render it
+        return fail(ctx, LFCUDA_ELIMIT, "instance update rejected: the rebuilt TLAS needs a traversal stack deeper than 64 entries; upload the scene again");
+    }
+    ctx->packed.stack_depth = depth;
+    ctx->packed.top_ref = res[0];
+    ctx->dev.top_ref = res[0];
+    return 0;
+}
+
+// Parity probe: the flat TLAS nodes the device holds (uploaded, or rebuilt by lfcuda_update_instances_device), in the reference's layout.
+int lfcuda_read_tlas_nodes(lfcuda_ctx* ctx, float* nodes_out, int32_t max_nodes, int32_t* num_nodes_out) {
+    if (!ctx || !ctx->have_scene || !ctx->tlas_ready || !nodes_out) return fail(ctx, LFCUDA_EINVAL, "no scene uploaded or NULL output");
+    const int n = 2 * ctx->dev.num_instances - 1;
+    if (max_nodes < n) return fail(ctx, LFCUDA_EINVAL, "output holds %d nodes, the TLAS has %d", max_nodes, n);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(nodes_out, ctx->d_flat_tlas, (size_t)9 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (num_nodes_out) *num_nodes_out = n;
     return 0;
 }
 

@@ -201,6 +201,11 @@ int lfcuda_group_update_instances(lfcuda_group* g, const float* transforms, int3
     if (!g) return LFCUDA_EINVAL;
     return for_all(g, [=](int, lfcuda_ctx* c) { return lfcuda_update_instances(c, transforms, num_instances, materials, num_materials, tlas_nodes, first_node, num_tlas_nodes); });
 }
+int lfcuda_group_update_instances_device(lfcuda_group* g, const float* transforms, int32_t num_instances, const float* materials, int32_t num_materials,
+                                         const int32_t* instance_material_ids) {
+    if (!g) return LFCUDA_EINVAL;
+    return for_all(g, [=](int, lfcuda_ctx* c) { return lfcuda_update_instances_device(c, transforms, num_instances, materials, num_materials, instance_material_ids); });
+}
 int lfcuda_group_set_params(lfcuda_group* g, const LfParams* p) {
     if (!g || !p) return LFCUDA_EINVAL;
     return for_all(g, [p](int, lfcuda_ctx* c) { return lfcuda_set_params(c, p); });

@@ -68,6 +68,9 @@ class CudaRenderer:
             self.h = None
             raise LfCudaError(f"CudaRenderer::Init failed: {msg}")
 
+    def SetDeviceTlasRebuild(self, on=True):
+        self.lib.lfhost_renderer_set_device_tlas(self.h, 1 if on else 0)
+
     def Update(self, dt=0.0):
         self.lib.lfhost_renderer_update(self.h, dt)
 

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "Camera.h"
 #include "GlobalState.h"
@@ -28,7 +29,7 @@ namespace LavaFrame
         , tileX(-1), tileY(-1), numTilesX(-1), numTilesY(-1)
         , tileWidth(scene->renderOptions.tileWidth), tileHeight(scene->renderOptions.tileHeight)
         , currentBuffer(0), frameCounter(1), sampleCounter(0)
-        , pixelRatio(1.0f), previewDof(false), previewDepth(2), previewW(0), previewH(0)
+        , pixelRatio(1.0f), deviceTlas(getenv("LF_DEVICE_TLAS") && atoi(getenv("LF_DEVICE_TLAS")) != 0), previewDof(false), previewDepth(2), previewW(0), previewH(0)
     {
     }
 
@@ -158,7 +159,13 @@ namespace LavaFrame
     void CudaRenderer::Update(float secondsElapsed)
     {
         if (!initialized) return;
-        if (scene->instancesModified) {          // Renderer::Update, Renderer.cpp:190-205
+        if (scene->instancesModified && deviceTlas) {
+            std::vector<int32_t> mats(scene->meshInstances.size());
+            for (size_t i = 0; i < mats.size(); i++) mats[i] = scene->meshInstances[i].materialID;
+            if (lfcuda_group_update_instances_device(group, reinterpret_cast<const float*>(scene->transforms.data()), (int)scene->transforms.size(),
+                                                     reinterpret_cast<const float*>(scene->materials.data()), (int)scene->materials.size(), mats.data()) != 0)
+                printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
+        } else if (scene->instancesModified) {   // Renderer::Update, Renderer.cpp:190-205
             int index = scene->bvhTranslator.topLevelIndex;
             int total = (int)scene->bvhTranslator.nodes.size();
             if (lfcuda_group_update_instances(group, reinterpret_cast<const float*>(scene->transforms.data()), (int)scene->transforms.size(),

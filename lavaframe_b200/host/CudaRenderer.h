@@ -47,6 +47,9 @@ namespace LavaFrame
         lfcuda_ctx* Context() const { return ctx; }                 // the context of the first device (preview, probes)
         lfcuda_group* Group() const { return group; }
         int NumDevices() const { return (int)devices.size(); }
+        // Instance edits: rebuild the TLAS on the device(s) from the matrices (lfcuda_update_instances_device) instead of uploading
+        // the TLAS Scene::RebuildInstances built on the host.  Same nodes, bit for bit; off by default (also: LF_DEVICE_TLAS=1).
+        void SetDeviceTlasRebuild(bool on) { deviceTlas = on; }
         bool Ok() const { return initialized && ctx != nullptr; }   // Init completed: scene uploaded, uniforms set, accumulation cleared
         const char* LastError() const;
         void Flush();                                            // execute every queued tile step now
@@ -70,6 +73,7 @@ namespace LavaFrame
         int tileX, tileY, numTilesX, numTilesY, tileWidth, tileHeight;
         int currentBuffer, frameCounter, sampleCounter;
         float pixelRatio;                // GlobalState.previewScale at Init (TiledRenderer.cpp:61)
+        bool deviceTlas;
         bool previewDof;                 // GlobalState.useDofInPreview at Init (#define USE_DOF, :90-91)
         int previewDepth;                // the preview shader's maxDepth uniform as Update last set it (:532)
         int previewW, previewH;          // size of the last preview drawn, 0 = none

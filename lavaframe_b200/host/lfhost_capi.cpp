@@ -85,6 +85,7 @@ void* lfhost_renderer_create_multi(void* s, const int* devices, int ndev) {
     r->Init();
     return r;
 }
+void lfhost_renderer_set_device_tlas(void* r, int on) { static_cast<CudaRenderer*>(r)->SetDeviceTlasRebuild(on != 0); }
 void lfhost_renderer_destroy(void* r) { delete static_cast<CudaRenderer*>(r); }
 int  lfhost_renderer_ok(void* r) { return static_cast<CudaRenderer*>(r)->Ok() ? 1 : 0; }
 const char* lfhost_renderer_error(void* r) { return static_cast<CudaRenderer*>(r)->LastError(); }

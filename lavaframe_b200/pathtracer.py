@@ -82,6 +82,22 @@ class PathTracer:
         self._ck(self.lib.lfcuda_update_instances(self.h, t.ctypes.data_as(fp), t.size // 16, m.ctypes.data_as(fp), m.size // 28,
                                                   n.ctypes.data_as(fp), int(first_node), n.size // 9), "lfcuda_update_instances")
 
+    def update_instances_device(self, transforms, materials=None, instance_material_ids=None):
+        """Instance edit with the TLAS rebuilt on the device (lfcuda_update_instances_device)."""
+        t = np.ascontiguousarray(transforms, np.float32).reshape(-1)
+        fp = C.POINTER(C.c_float)
+        m = np.ascontiguousarray(materials, np.float32).reshape(-1) if materials is not None else None
+        ids = np.ascontiguousarray(instance_material_ids, np.int32) if instance_material_ids is not None else None
+        self._ck(self.lib.lfcuda_update_instances_device(self.h, t.ctypes.data_as(fp), t.size // 16, m.ctypes.data_as(fp) if m is not None else None,
+                                                         m.size // 28 if m is not None else 0,
+                                                         ids.ctypes.data_as(C.POINTER(C.c_int32)) if ids is not None else None), "lfcuda_update_instances_device")
+
+    def read_tlas_nodes(self, num_instances):
+        out = np.empty((2 * num_instances - 1, 9), np.float32)
+        n = C.c_int32()
+        self._ck(self.lib.lfcuda_read_tlas_nodes(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), out.shape[0], C.byref(n)), "lfcuda_read_tlas_nodes")
+        return out[:n.value]
+
     # ---- hot path
     def clear(self):
         self._ck(self.lib.lfcuda_clear(self.h), "lfcuda_clear")

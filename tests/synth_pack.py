@@ -96,10 +96,11 @@ def chain_scene(path, n_tris=40, width=64, height=48, instances=((0.0, 0.0, 0.0)
     blas_lo, blas_hi = lo.min(axis=0), hi.max(axis=0)
     top = len(nodes)
     ninst = len(instances)
-    assert ninst == 2
+    assert ninst in (1, 2)
     boxes = [(blas_lo + np.array(t, np.float32), blas_hi + np.array(t, np.float32)) for t in instances]
-    nodes.append((*np.minimum(boxes[0][0], boxes[1][0]), *np.maximum(boxes[0][1], boxes[1][1]), top + 1, top + 2, 0))
-    for k in range(ninst):
+    if ninst == 2:
+        nodes.append((*np.minimum(boxes[0][0], boxes[1][0]), *np.maximum(boxes[0][1], boxes[1][1]), top + 1, top + 2, 0))
+    for k in range(ninst):                                           # (one instance: the TLAS root is its leaf)
         nodes.append((*boxes[k][0], *boxes[k][1], 0, 1 + k, -(k + 1)))   # TLAS leaf: (blasRoot, materialID, -(instance+1))
     nodes.append((0,) * 9)                                           # 2N reserved slots, 2N-1 used (bvh_translator.cpp:95-101)
     mats = [material(), material(albedo=(0.9, 0.3, 0.2)), material(albedo=(0.2, 0.4, 0.9), metallic=1.0, roughness=0.3)]

@@ -164,6 +164,33 @@ def test_instance_edit_vs_oracle_many_instances(gpu, tmp_path_factory, tmp_path,
     s.close()
 
 
+def test_instance_edit_with_device_tlas(gpu, tmp_path_factory, tmp_path, oracle_lib):
+    """CudaRenderer::SetDeviceTlasRebuild: the instance-edit path with the TLAS rebuilt on the device equals the oracle's render of the
+    scene the reference's host code re-flattened (c4_gold, 196 instances)."""
+    from scenes import gen_scenes
+    path = gen_scenes.c4_gold(str(tmp_path_factory.mktemp("c4gold_dev")))
+    s = lf.HostScene(path)
+    r = lf.CudaRenderer(s)
+    r.SetDeviceTlasRebuild(True)
+    r.Run(1)
+    v, _, _ = s.views()
+    T = np.ctypeslib.as_array(v.transforms, shape=(v.num_instances, 16)).copy()
+    rng = np.random.RandomState(9)
+    for idx in (3, 77, 150, 195):
+        mtx = T[idx].copy()
+        mtx[12:15] += rng.uniform(-1.5, 1.5, 3).astype(np.float32)
+        mtx[0] *= 1.3; mtx[10] *= 0.6
+        s.move_instance(idx, mtx)
+        r.Update(0.0); r.Render()
+    r.Run(2)
+    img = r.GetOutputBufferHDR()
+    ref = _oracle_image(s, tmp_path, "devtlas", 2)
+    differ = int((img != ref).any(axis=2).sum())
+    assert differ == 0, f"{differ} pixels differ from the oracle after instance edits with the device-built TLAS"
+    r.close()
+    s.close()
+
+
 def test_preview_while_camera_moves(cornell_scene, golden_dir):
     """TiledRenderer::Render draws the preview engine while camera->isMoving (TiledRenderer.cpp:327-333) at
     screenSize * GlobalState.previewScale; the image Present() would show must equal the reference's previewFBO."""
