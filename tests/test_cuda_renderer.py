@@ -221,6 +221,37 @@ def test_preview_while_camera_moves(cornell_scene, golden_dir):
     cornell_scene.set_preview(1.0, False)
 
 
+def _read_exr_bgr(path):
+    """Minimal reader of an uncompressed scan-line OpenEXR file with FLOAT channels B, G, R -> (H, W, 3) RGB float32."""
+    import struct
+    b = open(path, "rb").read()
+    assert b[:4] == bytes([0x76, 0x2f, 0x31, 0x01]) and b[4] == 2
+    pos, attrs = 8, {}
+    while b[pos] != 0:
+        e = b.index(b"\0", pos); name = b[pos:e].decode(); pos = e + 1
+        e = b.index(b"\0", pos); typ = b[pos:e].decode(); pos = e + 1
+        size, = struct.unpack_from("<i", b, pos); pos += 4
+        attrs[name] = (typ, b[pos:pos + size]); pos += size
+    pos += 1
+    assert attrs["compression"][1] == b"\0" and attrs["lineOrder"][1] == b"\0"
+    ch, names, p = attrs["channels"][1], [], 0
+    while ch[p] != 0:
+        e = ch.index(b"\0", p); names.append(ch[p:e].decode()); p = e + 1
+        assert struct.unpack_from("<i", ch, p)[0] == 2                     # FLOAT
+        p += 16
+    assert names == ["B", "G", "R"]
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    offs = struct.unpack_from(f"<{h}Q", b, pos)
+    img = np.empty((h, w, 3), np.float32)
+    for y in range(h):
+        yy, size = struct.unpack_from("<2i", b, offs[y])
+        assert yy == y and size == 3 * w * 4
+        planes = np.frombuffer(b, np.float32, 3 * w, offs[y] + 8).reshape(3, w)
+        img[y, :, 2], img[y, :, 1], img[y, :, 0] = planes[0], planes[1], planes[2]
+    return img
+
+
 def test_headless_cxx_driver(golden_dir, gpu, tmp_path):
     """lavaframe_b200/bin/lf_render: Main.cpp's Update -> Render loop on a CudaRenderer in pure C++ (no Python between the
     reference's loader, the drop-in class and the C ABI).  Its GetOutputBufferHDR image equals the llvmpipe golden within the
@@ -235,8 +266,8 @@ def test_headless_cxx_driver(golden_dir, gpu, tmp_path):
     n = int(g["nspp"])
     scene = gen_scenes.cornell_256(str(tmp_path / "cornell"))
     out = str(tmp_path / "img.f32")
-    png, bmp = str(tmp_path / "img.png"), str(tmp_path / "img.bmp")
-    res = subprocess.run([exe, scene, "--spp", str(n), "--out", out, "--png", png, "--bmp", bmp], check=True, capture_output=True, text=True, timeout=300)
+    png, bmp, exr = str(tmp_path / "img.png"), str(tmp_path / "img.bmp"), str(tmp_path / "img.exr")
+    res = subprocess.run([exe, scene, "--spp", str(n), "--out", out, "--png", png, "--bmp", bmp, "--exr", exr], check=True, capture_output=True, text=True, timeout=300)
     info = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert (info["width"], info["height"], info["spp"], info["tile_steps"]) == (256, 256, n, n)
     img = np.fromfile(out, np.float32).reshape(256, 256, 3)
@@ -247,6 +278,8 @@ def test_headless_cxx_driver(golden_dir, gpu, tmp_path):
     for f in (png, bmp):
         got = np.asarray(Image.open(f).convert("RGB"))
         assert got.shape == (256, 256, 3) and np.array_equal(got, want), f
+    # SaveFrameEXR (Export.h:57-152): the float image as B, G, R FLOAT planes, rows as GetOutputBufferHDR returns them (no flip)
+    assert np.array_equal(_read_exr_bgr(exr), img)
     # the same scene with 64x64 tiles: 16 tile steps per sample and a new `frame` (RNG seed) for every tile step, against the
     # reference's own tiled run on llvmpipe
     gt = np.load(os.path.join(golden_dir, "cornell_tiled_llvmpipe.npz"))
