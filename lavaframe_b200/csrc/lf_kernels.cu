@@ -100,13 +100,17 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 #define LF_TRACE_MINBLOCKS 9   // 56 registers: 9 CTAs x 128 threads fill the register file (10 -> 48 registers spills, +60 % time)
 #endif
 #ifndef LF_REFILL_MIN
-#define LF_REFILL_MIN 8
+#define LF_REFILL_MIN 12   // idle lanes that trigger a refill; 8 in round 1, re-swept with the half-parked leaf gather: 12 is +0.8 / +1.4 / +2.0 % on C2 / C4 / C3 (profiles/r2/r2h_ab_*)
 #endif
-#ifndef LF_LEAF_GATHER
-#define LF_LEAF_GATHER 3
+// The inner-node phase of a warp ends when parked lanes * LF_GATHER_DEN >= live lanes * LF_GATHER_NUM (parked = at a triangle leaf, an
+// instance entry / exit, or finished).  Round 1 used 1/3; re-swept in round 2 with the final kernels (profiles/r2/r2g_ab_*, r2h_ab_*).
+#ifndef LF_GATHER_NUM
+#define LF_GATHER_NUM 1
+#endif
+#ifndef LF_GATHER_DEN
+#define LF_GATHER_DEN 2
 #endif
 constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refill from the queue
-constexpr int kLeafGather = LF_LEAF_GATHER;   // leaf phase starts when live lanes / kLeafGather are parked at a leaf
 
 // Shared memory of a traversal CTA: the stacks [STACK][128] (16 KB at 32 entries) + the world-space rays [9][128] (4.5 KB).  Measured and
 // rejected in round 2 (profiles/r2/README.md): keeping only 12 stack entries in shared memory with a global overflow array, and
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         if (!__any_sync(FULL, alive)) break;
 
         // ---- phase 1: every lane steps through inner nodes; a lane that reaches anything else (triangle leaf, instance
-        // entry, end of a BLAS, end of the walk) parks there.  The phase ends when a third of the live lanes are parked
+        // entry, end of a BLAS, end of the walk) parks there.  The phase ends when half of the live lanes are parked
         // (or nobody can step): the expensive, rarer steps are then done by many lanes at once, while the inner-node
         // walk never waits for the slowest lane.
         bool rayDone = false;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         for (;;) {
             const bool canStep = alive && w.ref >= 0 && !w.axis;
             const unsigned stepMask = __ballot_sync(FULL, canStep);
-            if (stepMask == 0u || (liveLanes - __popc(stepMask)) * kLeafGather >= liveLanes) break;
+            if (stepMask == 0u || (liveLanes - __popc(stepMask)) * LF_GATHER_DEN >= liveLanes * LF_GATHER_NUM) break;
             if (canStep) {
                 Ray r;                                       // not read by an inner-node step
                 walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
