@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "Camera.h"
 #include "GlobalState.h"
@@ -29,7 +30,7 @@ namespace LavaFrame
         , tileX(-1), tileY(-1), numTilesX(-1), numTilesY(-1)
         , tileWidth(scene->renderOptions.tileWidth), tileHeight(scene->renderOptions.tileHeight)
         , currentBuffer(0), frameCounter(1), sampleCounter(0)
-        , pixelRatio(1.0f), deviceTlas(getenv("LF_DEVICE_TLAS") && atoi(getenv("LF_DEVICE_TLAS")) != 0), previewDof(false), previewDepth(2), previewW(0), previewH(0)
+        , pixelRatio(1.0f), deviceTlas(getenv("LF_DEVICE_TLAS") && atoi(getenv("LF_DEVICE_TLAS")) != 0), haveUniforms(false), previewDof(false), previewDepth(2), previewW(0), previewH(0)
     {
     }
 
@@ -71,6 +72,7 @@ namespace LavaFrame
         previewDepth = scene->renderOptions.maxDepth;
         previewW = previewH = 0;
 
+        haveUniforms = false;
         if (lfcuda_group_create(&group, devices.data(), (int)devices.size()) != 0) { group = nullptr; FailInit(); return; }
         ctx = lfcuda_group_ctx(group, 0);
         LfSceneView view;
@@ -85,17 +87,30 @@ namespace LavaFrame
     {
         LfParams params;
         LfCamera cam;
+        memset(&params, 0, sizeof params); memset(&cam, 0, sizeof cam);      // compared bytewise below
         lfhost::MakeParams(scene, &params);
         lfhost::MakeCamera(scene, &cam);
         const RenderOptions& ro = scene->renderOptions;      // postShader uniforms, TiledRenderer.cpp:539-553
         LfPostParams post;
+        memset(&post, 0, sizeof post);
         post.use_ca = ro.useCA ? 1 : 0; post.use_ca_distortion = ro.useCADistortion ? 1 : 0;
         post.ca_distance = ro.caDistance; post.ca_p1 = ro.caP1; post.ca_p2 = ro.caP2; post.ca_p3 = ro.caP3;
         post.use_vignette = ro.useVignette ? 1 : 0; post.vignette_intensity = ro.vignetteIntensity; post.vignette_power = ro.vignettePower;
-        if (lfcuda_group_set_params(group, &params) != 0 || lfcuda_group_set_camera(group, &cam) != 0 || lfcuda_group_set_post(group, &post) != 0) {
-            printf("CudaRenderer: %s\n", lfcuda_group_last_error(group));
-            return false;
+        // Update() runs once per tile step (4096 times for a 4096-spp single-tile render); the uniforms hardly ever change between
+        // two of them, and every group call is a round trip to one worker thread per device: only what changed is sent.
+        if (!haveUniforms || memcmp(&params, &lastParams, sizeof params) != 0) {
+            if (lfcuda_group_set_params(group, &params) != 0) { printf("CudaRenderer: %s\n", lfcuda_group_last_error(group)); return false; }
+            lastParams = params;
         }
+        if (!haveUniforms || memcmp(&cam, &lastCam, sizeof cam) != 0) {
+            if (lfcuda_group_set_camera(group, &cam) != 0) { printf("CudaRenderer: %s\n", lfcuda_group_last_error(group)); return false; }
+            lastCam = cam;
+        }
+        if (!haveUniforms || memcmp(&post, &lastPost, sizeof post) != 0) {
+            if (lfcuda_group_set_post(group, &post) != 0) { printf("CudaRenderer: %s\n", lfcuda_group_last_error(group)); return false; }
+            lastPost = post;
+        }
+        haveUniforms = true;
         return true;
     }
 
@@ -146,7 +161,7 @@ namespace LavaFrame
             return;
         }
         pending.push_back(Step{frameCounter, tileX, tileY, sampleCounter});
-        if (pending.size() >= 4096) FlushCompletedSamples();
+        if (pending.size() >= 256) FlushCompletedSamples();   // launches are asynchronous: the devices render while this loop goes on
     }
 
     float CudaRenderer::GetProgress() const

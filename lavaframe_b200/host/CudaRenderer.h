@@ -74,6 +74,8 @@ namespace LavaFrame
         int currentBuffer, frameCounter, sampleCounter;
         float pixelRatio;                // GlobalState.previewScale at Init (TiledRenderer.cpp:61)
         bool deviceTlas;
+        bool haveUniforms;               // the uniforms last sent to the devices (Update sends only what changed)
+        LfParams lastParams; LfCamera lastCam; LfPostParams lastPost;
         bool previewDof;                 // GlobalState.useDofInPreview at Init (#define USE_DOF, :90-91)
         int previewDepth;                // the preview shader's maxDepth uniform as Update last set it (:532)
         int previewW, previewH;          // size of the last preview drawn, 0 = none

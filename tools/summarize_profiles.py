@@ -72,7 +72,7 @@ def shares(tag):
         elif k == "k_generate":
             if args and args[0] == "1":
                 continue
-        elif k in ("k_read_probe",):
+        elif k in ("k_read_probe", "k_node_probe"):
             continue
         tot[k] += v
     T = sum(tot.values())
