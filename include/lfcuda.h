@@ -178,6 +178,8 @@ int  lfcuda_update_instances_device(lfcuda_ctx* ctx, const float* transforms, in
 int  lfcuda_read_tlas_nodes(lfcuda_ctx* ctx, float* nodes_out, int32_t max_nodes, int32_t* num_nodes_out);
 
 /* ---- per-frame uniforms (TiledRenderer::Init :222-227, ::Update :505-521) ----------------------- */
+/* Only a change of width / height re-creates (and thereby clears) the accumulation buffer and moves lfcuda_accum_device_ptr's address; tile
+ * size, depth, batch size and every other field leave the accumulated image alone (the reference updates them as plain uniforms). */
 int  lfcuda_set_params(lfcuda_ctx* ctx, const LfParams* params);
 int  lfcuda_set_camera(lfcuda_ctx* ctx, const LfCamera* camera);
 int  lfcuda_set_post(lfcuda_ctx* ctx, const LfPostParams* post);   /* NULL = defaults (no CA, no vignette) */

@@ -53,14 +53,31 @@ LFD void queue_push(int* queue, int* count, bool alive, int value) {
     if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
-LFD void store_state(const PathSoA& A, int s, const PathRegs& ps) {
-    A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
-    A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
-    A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
-    A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
-    A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
-    A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
-    A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+// The state of a path that has not bounced yet (pathtrace.glsl:210-216; renderer.glsl:43-62 made its ray and RNG).  `State` is zero-filled,
+// so the emission a directly seen analytic light adds "from the last surface" (:246-253) is matID 0's.
+LFD void initial_state(const DevScene& S, PathRegs& ps) {
+    ps.thr = mk3(1.0f); ps.rad = mk3(0.0f); ps.absn = mk3(0.0f); ps.bsdf_pdf = 0.f;
+    ps.stale = xyz(ldg4(S.materials + 1));
+}
+// Path state at the head of a shade kernel.  Bounce 0 starts from initial_state; `stale` is only ever read on an analytic-light hit, so
+// kernels of scenes without lights neither load nor store it.
+template <bool LIGHTS>
+LFD void load_path(const DevScene& S, const PathSoA& A, int s, int depth, PathRegs& ps) {
+    const float4 o = A.ray_o[s], d = A.ray_d[s];
+    const uint4 g = A.rng[s];
+    ps.ray.o = xyz(o); ps.ray.d = xyz(d);
+    ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
+    if (depth == 0) { initial_state(S, ps); return; }
+    const float4 th = A.thr[s], ra = A.rad[s], ab = A.absn[s];
+    ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab);
+    ps.stale = LIGHTS ? xyz(A.stale[s]) : mk3(0.f);
+}
+// The hit record ClosestHit left in the path state; state.fhp (closest_hit.glsl:139,143) is formed here, by full warps, instead of by the
+// few lanes of a traversal warp whose rays happen to end together - and is neither written nor re-read for paths that stop at this hit.
+LFD void load_hit(const DevScene& S, const PathSoA& A, int s, const Ray& ray, Hit& h) {
+    const float4 hf = A.hit_f[s]; const int4 hi = A.hit_i[s];
+    h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w;
+    hit_point(S, ray, h);
 }
 
 // ---------------------------------------------------------------------------------------------- generate
@@ -76,9 +93,11 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
             PathRegs ps;
             if (P.preview) ps.ray = preview_ray(P, lx, P.pv_y0 + ly, ps.rng);
             else ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
-            ps.thr = mk3(1.0f); ps.rad = mk3(0.0f); ps.absn = mk3(0.0f); ps.bsdf_pdf = 0.f;
-            ps.stale = xyz(ldg4(S.materials + 1));                 // State is zero-filled: matID 0's emission (pathtrace.glsl:213,253)
-            store_state(A, s, ps);
+            // throughput 1, radiance 0, absorption 0, bsdfSampleRec.pdf 0 and the stale emission are the same for every new path:
+            // they are not stored; the shade kernels of bounce 0 start from them (initial_state) instead of loading 64 bytes per path
+            A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+            A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
+            A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
             bump<COUNT>(cnt, C_SAMPLES);
         }
         queue_push(Q.active[0], count0, valid, s);
@@ -119,7 +138,7 @@ constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refil
 // its capacity: -1 % at best, and the extra live values push the any-hit kernel into spills at its 56-register limit.
 template <bool ANY, bool CULL, bool COUNT, int STACK>
 __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
-                                                       int* cursor, DevCounters* cnt) {
+                                                       int* cursor, const float4* __restrict__ neeT, DevCounters* cnt) {
     __shared__ int stack[STACK * kBlockThreads];
     __shared__ float wray[9 * kBlockThreads];           // world-space ray of each lane + 1/direction (restored when a BLAS is left)
     PlainStk stk;
@@ -239,11 +258,8 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         // ---- finished rays: write the result; shadow lanes go on with their second ray
         if (rayDone) {
             if (!ANY) {
-                Ray r = world_ray();
-                hit_point(S, r, hit);
-                A.hit_f[slot] = make_float4(hit.t, hit.u, hit.v, hit.lpdf);
+                A.hit_f[slot] = make_float4(hit.t, hit.u, hit.v, hit.lpdf);      // state.fhp is formed by the shade kernel (load_hit)
                 A.hit_i[slot] = make_int4(hit.tri, hit.inst, hit.light, hit.mat);
-                A.hit_p[slot] = make_float4(hit.fhp.x, hit.fhp.y, hit.fhp.z, 0.f);
                 alive = false;
             } else {
                 bool occluded = hit.light == 0;
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                     else hit.light = -1;
                 } else {
                     float4 ra = A.rad[slot];
-                    f3 rad = xyz(ra) + Li * xyz(A.sh_T[slot]);           // radiance += DirectLight(r, state) * throughput
+                    f3 rad = xyz(ra) + Li * xyz(neeT[slot]);             // radiance += DirectLight(r, state) * throughput
                     A.rad[slot] = make_float4(rad.x, rad.y, rad.z, 0.f);
                     alive = false;
                 }
@@ -265,6 +281,13 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
 }
 
 // ---------------------------------------------------------------------------------------------- shade
+// Order of the two passes after k_shade.  1: shadow, then sample: the throughput the NEE sum is multiplied with (pathtrace.glsl:266) is then
+// still what k_shade left in PathSoA::thr, so it is neither stored a second time (sh_T) nor fetched from a second array.  0: round 1's order.
+// (The fused kernel samples inside the shade kernel and keeps sh_T.)
+#ifndef LF_SHADOW_FIRST
+#define LF_SHADOW_FIRST 1
+#endif
+bool shadow_before_sample() { return LF_SHADOW_FIRST != 0; }
 #ifndef LF_SHADE_MINBLOCKS
 #define LF_SHADE_MINBLOCKS 5   // 96 registers.  ms of k_shade per 6 steps, C2 / C4: 5 CTAs per SM: 77.9 / 440, 6: 82.8 / 479, 7: 83.8 / 529 (profiles/r2/r2a_ab_*;
                                // round 1: 8: 93.9, 9: 97.3, 10: 107.7 on C2, profiles/r1_experiments/ab_shade_sample_ctas.txt): the kernel is latency-bound
@@ -286,13 +309,9 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
         if (i < count) {
             s = queue[i];
             PathRegs ps;
-            float4 o = A.ray_o[s], d = A.ray_d[s], th = A.thr[s], ra = A.rad[s], ab = A.absn[s], st = A.stale[s];
-            uint4 g = A.rng[s];
-            ps.ray.o = xyz(o); ps.ray.d = xyz(d); ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab); ps.stale = xyz(st);
-            ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
+            load_path<LIGHTS>(S, A, s, depth, ps);
             Hit h;
-            float4 hf = A.hit_f[s]; int4 hi = A.hit_i[s]; float4 hp = A.hit_p[s];
-            h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w; h.fhp = xyz(hp);
+            load_hit(S, A, s, ps.ray, h);
             Nee nee;
             Surf sf;
             f3 absnNext;
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
                 A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
                 if (nee.has0) { A.sh_d0[s] = make_float4(nee.d0.x, nee.d0.y, nee.d0.z, nee.m0); A.sh_c0[s] = make_float4(nee.c0.x, nee.c0.y, nee.c0.z, 0.f); }
                 if (nee.has1) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
-                A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);
+                if (!LF_SHADOW_FIRST) A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);   // else: A.thr, written below, is the same value
             } else if (surface) {
                 ps.rad = ps.rad + mk3(0.0f) * nee.T;              // radiance += DirectLight() * throughput with Li == 0 (pathtrace.glsl:266)
             }
@@ -312,8 +331,9 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
             A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
             if (wantSample) {
                 A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
-                A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+                if (LIGHTS) A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
                 A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+                A.hit_p[s] = make_float4(h.fhp.x, h.fhp.y, h.fhp.z, 0.f);                   // k_sample starts the next ray from it
                 const Mat& m = sf.mat;
                 A.sf0[s] = make_float4(sf.normal.x, sf.normal.y, sf.normal.z, sf.eta);
                 A.sf1[s] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.specular);
@@ -398,13 +418,9 @@ __global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScen
         if (i < count) {
             s = queue[i];
             PathRegs ps;
-            float4 o = A.ray_o[s], d = A.ray_d[s], th = A.thr[s], ra = A.rad[s], ab = A.absn[s], st = A.stale[s];
-            uint4 g = A.rng[s];
-            ps.ray.o = xyz(o); ps.ray.d = xyz(d); ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab); ps.stale = xyz(st);
-            ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
+            load_path<LIGHTS>(S, A, s, depth, ps);
             Hit h;
-            float4 hf = A.hit_f[s]; int4 hi = A.hit_i[s]; float4 hp = A.hit_p[s];
-            h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w; h.fhp = xyz(hp);
+            load_hit(S, A, s, ps.ray, h);
             Nee nee;
             Surf sf;
             f3 absnNext;
@@ -426,7 +442,7 @@ __global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScen
                     A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
                     A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
                     A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
-                    A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+                    if (LIGHTS) A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
                     A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
                 }
             }
@@ -480,8 +496,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_megakernel(DevScene S, DevPar
         if (!slot_pixel(P, q, lx, ly)) continue;
         PathRegs ps;
         ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
-        ps.thr = mk3(1.0f); ps.rad = mk3(0.0f); ps.absn = mk3(0.0f); ps.bsdf_pdf = 0.f;
-        ps.stale = xyz(ldg4(S.materials + 1));
+        initial_state(S, ps);
         bump<COUNT>(cnt, C_SAMPLES);
         for (int depth = 0; depth < P.max_depth; depth++) {
             Hit h;
@@ -598,12 +613,14 @@ void launch_node_probe(cudaStream_t stream, const float4* nodes, unsigned num_no
 // ---------------------------------------------------------------------------------------------- launchers
 template <bool CULL, bool COUNT>
 static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
+    // the throughput of the NEE sum: PathSoA::thr while k_sample has not run yet, the copy in sh_T otherwise
+    const float4* neeT = (LF_SHADOW_FIRST && !shade_is_fused(L)) ? L.soa.thr : L.soa.sh_T;
     if (L.stack_depth <= 32) {
-        if (which == 0) k_trace<false, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
-        else k_trace<true, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+        if (which == 0) k_trace<false, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
+        else k_trace<true, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
     } else {
-        if (which == 0) k_trace<false, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
-        else k_trace<true, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, L.counters);
+        if (which == 0) k_trace<false, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
+        else k_trace<true, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
     }
 }
 static void launch_trace(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {

@@ -38,6 +38,7 @@ void launch_shade(const LaunchCtx& L, int depth);
 void launch_sample(const LaunchCtx& L, int depth);
 bool shade_is_fused(const LaunchCtx& L);   // launch_shade runs both halves in one kernel, launch_sample is a no-op
 void launch_shadow(const LaunchCtx& L, int depth);
+bool shadow_before_sample();   // order of the two passes after launch_shade (see lf_kernels.cu LF_SHADOW_FIRST)
 void launch_accumulate(const LaunchCtx& L, float* accum);
 void launch_preview_store(const LaunchCtx& L, float* preview);
 void launch_megakernel(const LaunchCtx& L);

@@ -355,8 +355,9 @@ int run_batch(lfcuda_ctx* ctx, int first_frame, int nframes, int stride, int til
         for (int d = 0; d < D.max_depth; d++) {
             { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, d); }
             { StageTimer t(ctx, LF_STAGE_SHADE); launch_shade(L, d); }
+            if (shadow_before_sample()) { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
             if (d + 1 < D.max_depth && !shade_is_fused(L)) { StageTimer t(ctx, LF_STAGE_SAMPLE); launch_sample(L, d); }
-            { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
+            if (!shadow_before_sample()) { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
         }
     }
     if (accumulate) { StageTimer t(ctx, LF_STAGE_ACCUMULATE); launch_accumulate(L, ctx->d_accum); }
@@ -796,8 +797,9 @@ int lfcuda_render_preview(lfcuda_ctx* ctx, int32_t pv_width, int32_t pv_height, 
         for (int d = 0; d < D.max_depth; d++) {
             { StageTimer t(ctx, LF_STAGE_EXTEND); launch_extend(L, d); }
             { StageTimer t(ctx, LF_STAGE_SHADE); launch_shade(L, d); }
+            if (shadow_before_sample()) { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
             if (d + 1 < D.max_depth && !shade_is_fused(L)) { StageTimer t(ctx, LF_STAGE_SAMPLE); launch_sample(L, d); }
-            { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
+            if (!shadow_before_sample()) { StageTimer t(ctx, LF_STAGE_SHADOW); launch_shadow(L, d); }
         }
         { StageTimer t(ctx, LF_STAGE_ACCUMULATE); launch_preview_store(L, ctx->d_preview); }
         CK(cudaGetLastError());

@@ -47,6 +47,29 @@ def test_main_loop_protocol(cornell_scene, golden_dir):
     r.close()
 
 
+def test_failed_init_is_reported_not_hung(cornell_scene):
+    """A renderer whose Init fails (here: a device that does not exist) says so: Ok() is false, LastError() has the text, the Main.cpp loop
+    refuses to spin on a sample counter that will never advance, the output buffers are black, and nothing leaks or crashes on destruction."""
+    with pytest.raises(lf.LfCudaError, match="out of range|no CUDA device"):
+        lf.CudaRenderer(cornell_scene, device=9999)
+    with pytest.raises(lf.LfCudaError):
+        lf.CudaRenderer(cornell_scene, devices=[0, 9999])
+    lib = cornell_scene.lib
+    h = lib.lfhost_renderer_create(cornell_scene.h, 9999)          # the raw object, as a C++ caller would hold it
+    assert lib.lfhost_renderer_ok(h) == 0
+    assert lib.lfhost_renderer_error(h)
+    assert lib.lfhost_renderer_run(h, 4) == -1
+    import ctypes as C
+    w, hh = C.c_int(), C.c_int()
+    out = np.ones((256, 256, 3), np.float32)
+    lib.lfhost_renderer_output_hdr(h, out.ctypes.data_as(C.c_void_p), C.byref(w), C.byref(hh))
+    assert (w.value, hh.value) == (256, 256) and not out.any()
+    lib.lfhost_renderer_destroy(h)
+    r = lf.CudaRenderer(cornell_scene)                             # and the scene is still usable
+    assert r.Run(1) == 1
+    r.close()
+
+
 def test_renderer_equals_c_abi(cornell_scene, golden_dir):
     """The C++ class adds only bookkeeping: same bits as direct lfcuda_render_frames calls."""
     r = lf.CudaRenderer(cornell_scene)
