@@ -98,7 +98,7 @@ LFD float rnd(Rng& s) {
 // ---------------------------------------------------------------------------------------------- records
 struct Ray { f3 o, d; };
 struct Hit {
-    float t, u, v;             // uvt.z, uvt.x, uvt.y
+    float t, u, v, lpdf;       // uvt.z, uvt.x, uvt.y; emitter pdf
     int tri, inst, light, mat; // triangle ref, instance, analytic light index (-1 = surface or miss), material
     f3 fhp;                    // state.fhp (world)
 };
@@ -201,17 +201,7 @@ struct Walk {                  // traversal registers of one ray
     bool axis;                 // some component of idir is infinite: AABBIntersect takes its NaN-exact form
 };
 
-LFD void hit_clear(Hit& hit) { hit.light = -1; hit.tri = -1; hit.inst = -1; hit.mat = -1; hit.u = hit.v = 0.f; hit.t = kINF; }
-
-// lightSampleRec.pdf of an analytic light hit directly at distance t (closest_hit.glsl:41-44 quad, :57-58 sphere).  The reference forms it
-// inside ClosestHit; it depends only on the light, the ray direction and the final t, so it is formed where it is used (shade_nonsurface).
-LFD float light_pdf(const LightRec& L, f3 rd, float t) {
-    if (L.type == 0.f) {
-        float cosTheta = dot(-rd, L.normal);
-        return fdiv(t * t, L.area * cosTheta);
-    }
-    return fdiv(t * t, L.area);
-}
+LFD void hit_clear(Hit& hit) { hit.light = -1; hit.tri = -1; hit.inst = -1; hit.mat = -1; hit.u = hit.v = 0.f; hit.lpdf = 0.f; hit.t = kINF; }
 
 // Analytic lights first (closest_hit.glsl:13-67, anyhit.glsl:11-46).  ANY: returns true when a light blocks the ray.
 template <bool ANY, bool COUNT>
@@ -225,7 +215,12 @@ LFD bool test_lights(const DevScene& S, const Ray& r, float maxDist, Hit& hit, D
             if (ANY) { if (d > 0.0f && d < maxDist) return true; }
             else {
                 if (d < 0.f) d = kINF;
-                if (d < hit.t) { hit.t = d; hit.light = i; }
+                if (d < hit.t) {
+                    hit.t = d;
+                    float cosTheta = dot(-r.d, L.normal);
+                    hit.lpdf = fdiv(d * d, L.area * cosTheta);
+                    hit.light = i;
+                }
             }
         }
         if (L.type == 1.f) {
@@ -233,7 +228,7 @@ LFD bool test_lights(const DevScene& S, const Ray& r, float maxDist, Hit& hit, D
             if (ANY) { if (d > 0.0f && d < maxDist) return true; }
             else {
                 if (d < 0.f) d = kINF;
-                if (d < hit.t) { hit.t = d; hit.light = i; }
+                if (d < hit.t) { hit.t = d; hit.lpdf = fdiv(d * d, L.area); hit.light = i; }
             }
         }
     }

@@ -72,31 +72,11 @@ LFD void load_path(const DevScene& S, const PathSoA& A, int s, int depth, PathRe
     ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab);
     ps.stale = LIGHTS ? xyz(A.stale[s]) : mk3(0.f);
 }
-// The analytic lights are the first thing ClosestHit / AnyHit look at (closest_hit.glsl:13-67, anyhit.glsl:11-46), before the walk.  For the
-// wavefront that part runs in the DENSE kernel that creates the ray: the nearest light hit of a new closest-hit ray travels in the .w lanes of
-// ray_o / ray_d (t, light index) and k_trace starts its walk from it; an NEE candidate that a light blocks is dropped in the shade kernel and
-// never queued.  In k_trace the same loop ran for the 12-16 lanes of a refill at a time.
-template <bool COUNT>
-LFD void store_ray(const DevScene& S, const PathSoA& A, int s, const Ray& r, DevCounters* cnt) {
-    Hit h0;
-    hit_clear(h0);
-    test_lights<false, COUNT>(S, r, 0.f, h0, cnt);
-    A.ray_o[s] = make_float4(r.o.x, r.o.y, r.o.z, h0.t);
-    A.ray_d[s] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(h0.light));
-}
-template <bool COUNT>
-LFD void drop_nee_blocked_by_lights(const DevScene& S, Nee& nee, DevCounters* cnt) {
-    if (S.num_lights == 0) return;
-    Hit dummy;
-    Ray r; r.o = nee.origin;
-    if (nee.has0) { r.d = nee.d0; if (test_lights<true, COUNT>(S, r, nee.m0, dummy, cnt)) nee.has0 = false; }
-    if (nee.has1) { r.d = nee.d1; if (test_lights<true, COUNT>(S, r, nee.m1, dummy, cnt)) nee.has1 = false; }
-}
 // The hit record ClosestHit left in the path state; state.fhp (closest_hit.glsl:139,143) is formed here, by full warps, instead of by the
 // few lanes of a traversal warp whose rays happen to end together - and is neither written nor re-read for paths that stop at this hit.
 LFD void load_hit(const DevScene& S, const PathSoA& A, int s, const Ray& ray, Hit& h) {
     const float4 hf = A.hit_f[s]; const int4 hi = A.hit_i[s];
-    h.t = hf.x; h.u = hf.y; h.v = hf.z; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w;
+    h.t = hf.x; h.u = hf.y; h.v = hf.z; h.lpdf = hf.w; h.tri = hi.x; h.inst = hi.y; h.light = hi.z; h.mat = hi.w;
     hit_point(S, ray, h);
 }
 
@@ -115,7 +95,8 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
             else ps.ray = camera_ray(P, lx, ly, P.first_frame + fi * P.frame_stride, ps.rng);
             // throughput 1, radiance 0, absorption 0, bsdfSampleRec.pdf 0 and the stale emission are the same for every new path:
             // they are not stored; the shade kernels of bounce 0 start from them (initial_state) instead of loading 64 bytes per path
-            store_ray<COUNT>(S, A, s, ps.ray, cnt);
+            A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+            A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
             A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
             bump<COUNT>(cnt, C_SAMPLES);
         }
@@ -188,13 +169,16 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
     };
     auto world_ray = [&]() { Ray r; r.o = mk3(wr[0], wr[kBlockThreads], wr[2 * kBlockThreads]);
                              r.d = mk3(wr[3 * kBlockThreads], wr[4 * kBlockThreads], wr[5 * kBlockThreads]); return r; };
-    // start the walk of ray r
-    auto begin_ray = [&](const Ray& r) {
+    // start the walk of ray r; returns false when the ray is already decided (ANY: an analytic light blocks it)
+    auto begin_ray = [&](const Ray& r) -> bool {
         wr[0] = r.o.x; wr[kBlockThreads] = r.o.y; wr[2 * kBlockThreads] = r.o.z;
         wr[3 * kBlockThreads] = r.d.x; wr[4 * kBlockThreads] = r.d.y; wr[5 * kBlockThreads] = r.d.z;
-        bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);                    // (the analytic lights were tested where the ray was made)
+        if (!ANY) hit_clear(hit);
+        bump<COUNT>(cnt, ANY ? C_RAYS_SHADOW : C_RAYS_CLOSEST);
+        if (test_lights<ANY, COUNT>(S, r, maxDist, hit, cnt)) return false;
         walk_begin(S, r, w, stk);
         wr[6 * kBlockThreads] = w.idir.x; wr[7 * kBlockThreads] = w.idir.y; wr[8 * kBlockThreads] = w.idir.z;
+        return true;
     };
 
     for (;;) {
@@ -216,13 +200,10 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                     Li = mk3(0.0f);
                     r = shadow_ray(shPhase);
                 } else {
-                    const float4 o4 = A.ray_o[slot], d4 = A.ray_d[slot];
-                    r.o = xyz(o4); r.d = xyz(d4);
-                    hit_clear(hit);
-                    hit.t = o4.w; hit.light = __float_as_int(d4.w);            // the nearest analytic light, if any (store_ray)
+                    r.o = xyz(A.ray_o[slot]); r.d = xyz(A.ray_d[slot]);
                 }
-                begin_ray(r);
-                if (ANY) hit.light = -1;                                       // -1: nothing in the way so far, 0: occluded
+                if (!begin_ray(r)) { w.ref = kRefSentinel; w.inBlas = false; hit.light = 0; }   // decided: occluded by a light
+                else if (ANY) hit.light = -1;
             }
         }
         if (!__any_sync(FULL, alive)) break;
@@ -277,7 +258,7 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         // ---- finished rays: write the result; shadow lanes go on with their second ray
         if (rayDone) {
             if (!ANY) {
-                A.hit_f[slot] = make_float4(hit.t, hit.u, hit.v, 0.f);           // state.fhp is formed by the shade kernel (load_hit)
+                A.hit_f[slot] = make_float4(hit.t, hit.u, hit.v, hit.lpdf);      // state.fhp is formed by the shade kernel (load_hit)
                 A.hit_i[slot] = make_int4(hit.tri, hit.inst, hit.light, hit.mat);
                 alive = false;
             } else {
@@ -286,8 +267,8 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                 if (shPhase == 0 && (shMask & 2)) {
                     shPhase = 1;
                     Ray r = shadow_ray(1);
-                    begin_ray(r);
-                    hit.light = -1;
+                    if (!begin_ray(r)) { w.ref = kRefSentinel; w.inBlas = false; hit.light = 0; }
+                    else hit.light = -1;
                 } else {
                     float4 ra = A.rad[slot];
                     f3 rad = xyz(ra) + Li * xyz(neeT[slot]);             // radiance += DirectLight(r, state) * throughput
@@ -335,7 +316,6 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
             Surf sf;
             f3 absnNext;
             const bool surface = shade_hit<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, sf, absnNext, cnt);
-            if (LIGHTS) drop_nee_blocked_by_lights<COUNT>(S, nee, cnt);
             wantSample = surface && !lastBounce;
             wantShadow = nee.has0 || nee.has1;
             if (wantShadow) {
@@ -371,8 +351,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
 #ifndef LF_SAMPLE_MINBLOCKS
 #define LF_SAMPLE_MINBLOCKS 6   // ms of k_sample per 6 C2 steps: 6 CTAs per SM 26.3, 8: 30.4 (profiles/r2/r2d_ab_c2_full_shade4s6.json)
 #endif
-template <bool COUNT>
-__global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevScene S, DevParams P, PathSoA A, Queues Q, int depth, DevCounters* cnt) {
+__global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
     const int count = Q.counts[4 * Q.stride + depth];
     int* next = (depth & 1) ? Q.active[0] : Q.active[1];
     int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
@@ -401,7 +380,8 @@ __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevScene S,
             alive = shade_sample(P, depth, ps, sf, xyz(hp), xyz(f4v));
             A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
             if (alive) {
-                store_ray<COUNT>(S, A, s, ps.ray, cnt);
+                A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+                A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
                 A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
                 A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
             }
@@ -445,7 +425,6 @@ __global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScen
             Surf sf;
             f3 absnNext;
             const bool surface = shade_hit<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, sf, absnNext, cnt);
-            if (LIGHTS) drop_nee_blocked_by_lights<COUNT>(S, nee, cnt);
             wantShadow = nee.has0 || nee.has1;
             if (wantShadow) {
                 A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
@@ -460,7 +439,8 @@ __global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScen
                 alive = shade_sample(P, depth, ps, sf, h.fhp, absnNext);
                 if (alive) {
                     A.thr[s] = make_float4(ps.thr.x, ps.thr.y, ps.thr.z, ps.bsdf_pdf);
-                    store_ray<COUNT>(S, A, s, ps.ray, cnt);
+                    A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+                    A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
                     A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
                     if (LIGHTS) A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
                     A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
@@ -635,20 +615,12 @@ template <bool CULL, bool COUNT>
 static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
     // the throughput of the NEE sum: PathSoA::thr while k_sample has not run yet, the copy in sh_T otherwise
     const float4* neeT = (LF_SHADOW_FIRST && !shade_is_fused(L)) ? L.soa.thr : L.soa.sh_T;
-    // persistent grid = exactly the CTAs that are resident at once: what the occupancy calculator gives for this kernel's registers and shared
-    // memory (closest-hit: 56 registers -> 9 per SM; any-hit, without its light loop: 48 -> 10; 64-entry stacks: 5 / 6), capped by LF_CTAS_PER_SM
-    auto grid = [&](auto kernel) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
-        if (L.max_ctas_per_sm > 0 && per_sm > L.max_ctas_per_sm) per_sm = L.max_ctas_per_sm;
-        return L.sm_count * per_sm;
-    };
     if (L.stack_depth <= 32) {
-        if (which == 0) k_trace<false, CULL, COUNT, 32><<<grid(k_trace<false, CULL, COUNT, 32>), kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
-        else k_trace<true, CULL, COUNT, 32><<<grid(k_trace<true, CULL, COUNT, 32>), kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
+        if (which == 0) k_trace<false, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
+        else k_trace<true, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
     } else {
-        if (which == 0) k_trace<false, CULL, COUNT, 64><<<grid(k_trace<false, CULL, COUNT, 64>), kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
-        else k_trace<true, CULL, COUNT, 64><<<grid(k_trace<true, CULL, COUNT, 64>), kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
+        if (which == 0) k_trace<false, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
+        else k_trace<true, CULL, COUNT, 64><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
     }
 }
 static void launch_trace(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
@@ -757,8 +729,7 @@ void launch_shade(const LaunchCtx& L, int depth) {
 }
 void launch_sample(const LaunchCtx& L, int depth) {
     if (shade_is_fused(L)) return;                     // the BSDF sample ran inside the shade kernel
-    if (L.count) k_sample<true><<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
-    else k_sample<false><<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth, L.counters);
+    k_sample<<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
 }
 void launch_shadow(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;

@@ -26,7 +26,7 @@ struct LaunchCtx {
     DevCounters* counters;
     cudaStream_t stream;
     int sm_count;
-    int max_ctas_per_sm;     // cap on the resident CTAs per SM of the persistent traversal kernels (0 = what the occupancy calculator gives)
+    int persistent_blocks;   // CTAs of the persistent traversal kernels (multiple of the SM count)
     int stack_depth;         // traversal stack entries the scene needs (<= 64)
     bool cull, count;
     const SortCtx* sort = nullptr;   // non-null = sort the extend queue of bounces >= 1

@@ -53,7 +53,7 @@ LFD bool shade_hit(const DevScene& S, const DevParams& P, int depth, PathRegs& p
         ps.rad = ps.rad + ps.stale * ps.thr;
         LightRec L = load_light(S, hit.light);
         f3 Le = L.emission;
-        if (depth != 0) Le = powerHeuristic(ps.bsdf_pdf, light_pdf(L, rd, t)) * L.emission;   // EmitterSample, sampling.glsl:271-282
+        if (depth != 0) Le = powerHeuristic(ps.bsdf_pdf, hit.lpdf) * L.emission;   // EmitterSample, sampling.glsl:271-282
         ps.rad = ps.rad + Le * ps.thr;
         return false;
     }

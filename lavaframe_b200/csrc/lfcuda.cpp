@@ -99,9 +99,8 @@ struct lfcuda_ctx {
     uint64_t launches = 0;
     bool sort_rays = false;               // LF_SORT_RAYS=1|2|3: ray-sort experiment (lf_kernels.h SortCtx)
     SortCtx sort;
-    int ctas_per_sm = 0;                  // cap on the CTAs per SM of the persistent traversal kernels (LF_CTAS_PER_SM; 0 = their occupancy: the closest-hit
-                                          // kernel's 56 registers x 128 threads x 9 CTAs fill the register file exactly - measured: 8 -> 9 = -5 %, 10 needs 48
-                                          // registers and spills, +60 % - the any-hit kernel needs 48 since its light loop moved to the shade kernel: 10)
+    int ctas_per_sm = 9;                  // CTAs per SM of the persistent traversal kernels: 9 x 128 threads x 56 registers fill the
+                                          // register file exactly (measured: 8 -> 9 = -5 % extend/shadow time; 10 needs 48 registers and spills, +60 %)
 
     // NCCL (function table: process-wide g_nccl)
     void* comm = nullptr;
@@ -334,7 +333,8 @@ int check_ready(lfcuda_ctx* ctx) {
 void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
     L.scene = c->dev; L.params = D; L.soa = c->soa; L.queues = c->queues; L.counters = c->d_counters; L.stream = c->stream;
     L.sm_count = c->prop.multiProcessorCount;
-    L.max_ctas_per_sm = c->ctas_per_sm;
+    // the 64-entry stack variant needs 38.4 KB of shared memory per CTA: 5 CTAs per SM are resident, not 9
+    L.persistent_blocks = L.sm_count * (c->packed.stack_depth > 32 ? std::min(c->ctas_per_sm, 5) : c->ctas_per_sm);
     L.stack_depth = c->packed.stack_depth;
     L.cull = !c->params.no_cull;
     L.count = c->params.count_work != 0;
