@@ -1,6 +1,6 @@
-"""GPU tests of the experiment knobs that are OFF by default (run only with LF_TEST_EXPERIMENTS=1): an experiment may change speed,
-never a pixel.  LF_SORT_RAYS (bit 0: counting sort of the extend queue, bit 1: of the shadow queue, by origin cell and direction octant, lf_kernels.h SortCtx) was written
-after this round's GPU budget was spent; this test is its first check and is part of the next round's first gpurun call."""
+"""GPU tests of the experiment knobs that are OFF by default: an experiment may change speed, never a pixel.  LF_SORT_RAYS (bit 0: counting
+sort of the extend queue, bit 1: of the shadow queue, by origin cell and direction octant, lf_kernels.h SortCtx) was measured in round 2 and
+rejected (slower on every workload, profiles/README.md); the kernels stay behind the environment variable, and this test keeps them honest."""
 import os
 import subprocess
 import sys
@@ -10,7 +10,7 @@ import pytest
 
 import lavaframe_b200 as lf
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("LF_TEST_EXPERIMENTS") != "1", reason="experiment knobs: set LF_TEST_EXPERIMENTS=1")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RENDER = """
