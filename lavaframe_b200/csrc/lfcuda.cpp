@@ -345,6 +345,7 @@ void make_launch_ctx(lfcuda_ctx* c, LaunchCtx& L, const DevParams& D) {
 int run_batch(lfcuda_ctx* ctx, int first_frame, int nframes, int stride, int tile_x, int tile_y, bool accumulate) {
     DevParams D;
     fill_dev_params(ctx, D, first_frame, nframes, stride, tile_x, tile_y);
+    if (D.max_depth <= 0) return 0;   // maxDepth 0: the bounce loop never runs (pathtrace.glsl:218), every sample adds zero radiance
     LaunchCtx L;
     make_launch_ctx(ctx, L, D);
     if (ctx->params.kernel_mode == 1) {

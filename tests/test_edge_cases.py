@@ -76,7 +76,7 @@ def test_tiles_that_do_not_divide_the_frame(tracer, golden_dir, name):
 
 
 @pytest.mark.parametrize("params", [
-    dict(max_depth=1), dict(max_depth=2, enable_rr=0), dict(enable_rr=1, rr_depth=0), dict(max_depth=8, enable_rr=0), dict(use_envmap=0),
+    dict(max_depth=0), dict(max_depth=1), dict(max_depth=2, enable_rr=0), dict(enable_rr=1, rr_depth=0), dict(max_depth=8, enable_rr=0), dict(use_envmap=0),
 ])
 @pytest.mark.parametrize("name", ["c2mini", "c3mini"])
 def test_uniform_extremes(tracer, golden_dir, name, params):
