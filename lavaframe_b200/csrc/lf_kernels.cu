@@ -123,11 +123,20 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 #endif
 // The inner-node phase of a warp ends when parked lanes * LF_GATHER_DEN >= live lanes * LF_GATHER_NUM (parked = at a triangle leaf, an
 // instance entry / exit, or finished).  Round 1 used 1/3; re-swept in round 2 with the final kernels (profiles/r2/r2g_ab_*, r2h_ab_*).
+#ifndef LF_STEPS_PER_CHECK
+#define LF_STEPS_PER_CHECK 1
+#endif
 #ifndef LF_GATHER_NUM
 #define LF_GATHER_NUM 1
 #endif
 #ifndef LF_GATHER_DEN
 #define LF_GATHER_DEN 2
+#endif
+#ifndef LF_GATHER_NUM_ANY      // the any-hit (shadow) kernel's threshold, separately tunable
+#define LF_GATHER_NUM_ANY LF_GATHER_NUM
+#endif
+#ifndef LF_GATHER_DEN_ANY
+#define LF_GATHER_DEN_ANY LF_GATHER_DEN
 #endif
 constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refill from the queue
 
@@ -217,11 +226,17 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
         for (;;) {
             const bool canStep = alive && w.ref >= 0 && !w.axis;
             const unsigned stepMask = __ballot_sync(FULL, canStep);
-            if (stepMask == 0u || (liveLanes - __popc(stepMask)) * LF_GATHER_DEN >= liveLanes * LF_GATHER_NUM) break;
+            if (stepMask == 0u || (liveLanes - __popc(stepMask)) * (ANY ? LF_GATHER_DEN_ANY : LF_GATHER_DEN) >= liveLanes * (ANY ? LF_GATHER_NUM_ANY : LF_GATHER_NUM)) break;
             if (canStep) {
                 Ray r;                                       // not read by an inner-node step
                 walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
             }
+#if LF_STEPS_PER_CHECK >= 2   // experiment: the phase-end test (ballot, popc, compare: a tenth of the step) only every second step
+            if (alive && w.ref >= 0 && !w.axis) {
+                Ray r;
+                walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+            }
+#endif
         }
         // ---- phase 1x: lanes whose ray is parallel to an axis (1 / d infinite: the slab test takes its NaN-exact form, lf_device.cuh
         // AABBIntersect) park at inner nodes too and take ONE step here per round.  Such rays are vanishingly rare outside hand-built
