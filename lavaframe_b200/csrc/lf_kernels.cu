@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
 // The inner-node phase of a warp ends when parked lanes * LF_GATHER_DEN >= live lanes * LF_GATHER_NUM (parked = at a triangle leaf, an
 // instance entry / exit, or finished).  Round 1 used 1/3; re-swept in round 2 with the final kernels (profiles/r2/r2g_ab_*, r2h_ab_*).
 #ifndef LF_STEPS_PER_CHECK
-#define LF_STEPS_PER_CHECK 1
+#define LF_STEPS_PER_CHECK 3   // inner steps per phase-end test: 1 -> 2 = +1.3 / +1.3 / +1.2 % on C2 / C4 / C3 (profiles/r2/r2p_ab_*); 3: another +0.6 % on C4, +2 % on C1, C2 unchanged; 4: no better (r2q_ab_*)
 #endif
 #ifndef LF_GATHER_NUM
 #define LF_GATHER_NUM 1
@@ -231,12 +231,14 @@ __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(Dev
                 Ray r;                                       // not read by an inner-node step
                 walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
             }
-#if LF_STEPS_PER_CHECK >= 2   // experiment: the phase-end test (ballot, popc, compare: a tenth of the step) only every second step
-            if (alive && w.ref >= 0 && !w.axis) {
-                Ray r;
-                walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+            // the phase-end test above (ballot, popc, compare, branch) is a tenth of an inner step: it runs every LF_STEPS_PER_CHECK steps only
+#pragma unroll
+            for (int k = 1; k < LF_STEPS_PER_CHECK; k++) {
+                if (alive && w.ref >= 0 && !w.axis) {
+                    Ray r;
+                    walk_step<ANY, CULL, COUNT, 1>(S, r, w, ANY ? maxDist : hit.t, stk, cnt);
+                }
             }
-#endif
         }
         // ---- phase 1x: lanes whose ray is parallel to an axis (1 / d infinite: the slab test takes its NaN-exact form, lf_device.cuh
         // AABBIntersect) park at inner nodes too and take ONE step here per round.  Such rays are vanishingly rare outside hand-built

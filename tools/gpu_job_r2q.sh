@@ -1,0 +1,15 @@
+# Round 2 (1 GPU): GPU suite with 2 inner steps per phase-end test (default), then 3 / 4 steps and the neighbouring thresholds.
+tag=${1:-r2q}
+out=gpurun_out
+mkdir -p $out
+( time timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 ) > $out/${tag}_pytest_gpu.txt 2>&1
+tail -4 $out/${tag}_pytest_gpu.txt
+ab() {
+  w=$1; name=$2; shift; shift
+  env "$@" timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-llvmpipe --no-c5 --workload $w > $out/${tag}_ab_${w}_$name.json 2> $out/${tag}_ab_${w}_$name.err
+  echo "== $w $name"; python tools/bench_brief.py < $out/${tag}_ab_${w}_$name.json | cut -c1-200
+}
+for w in c2_full c4_stress c3_full c1; do
+  ab $w default LF_DUMMY=1
+  for v in steps3 steps4 s2g25 s3g25 s2r16; do [ -f ab/$v.so ] && ab $w $v LF_LFCUDA_SO=$PWD/ab/$v.so; done
+done
