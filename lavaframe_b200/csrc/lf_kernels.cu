@@ -72,6 +72,17 @@ LFD void load_path(const DevScene& S, const PathSoA& A, int s, int depth, PathRe
     ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab);
     ps.stale = LIGHTS ? xyz(A.stale[s]) : mk3(0.f);
 }
+// The shadow request of a surface hit.  A single candidate always goes into slot 0 of the request, whichever kind it is (with one ray the
+// order of the sum Li = 0 + c is the same), so that the common request touches two 32-byte records; with both, the environment ray is 0.
+LFD void store_nee(const PathSoA& A, int s, const Nee& nee) {
+    const bool both = nee.has0 && nee.has1, first1 = !nee.has0;       // first1: the only candidate is the analytic light's
+    const f3 d0 = first1 ? nee.d1 : nee.d0, c0 = first1 ? nee.c1 : nee.c0;
+    const float m0 = first1 ? nee.m1 : nee.m0;
+    A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float(both ? 3 : 1));
+    A.sh_d0[s] = make_float4(d0.x, d0.y, d0.z, m0);
+    A.sh_c0[s] = make_float4(c0.x, c0.y, c0.z, 0.f);
+    if (both) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
+}
 // The hit record ClosestHit left in the path state; state.fhp (closest_hit.glsl:139,143) is formed here, by full warps, instead of by the
 // few lanes of a traversal warp whose rays happen to end together - and is neither written nor re-read for paths that stop at this hit.
 LFD void load_hit(const DevScene& S, const PathSoA& A, int s, const Ray& ray, Hit& h) {
@@ -147,7 +158,7 @@ constexpr int kRefillMin = LF_REFILL_MIN;     // idle lanes that trigger a refil
 // its capacity: -1 % at best, and the extra live values push the any-hit kernel into spills at its 56-register limit.
 template <bool ANY, bool CULL, bool COUNT, int STACK>
 __global__ void __launch_bounds__(kBlockThreads, LF_TRACE_MINBLOCKS) k_trace(DevScene S, PathSoA A, const int* __restrict__ queue, const int* __restrict__ countp,
-                                                       int* cursor, const float4* __restrict__ neeT, DevCounters* cnt) {
+                                                       int* cursor, Pair<float4> neeT, DevCounters* cnt) {
     __shared__ int stack[STACK * kBlockThreads];
     __shared__ float wray[9 * kBlockThreads];           // world-space ray of each lane + 1/direction (restored when a BLAS is left)
     PlainStk stk;
@@ -336,9 +347,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
             wantSample = surface && !lastBounce;
             wantShadow = nee.has0 || nee.has1;
             if (wantShadow) {
-                A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
-                if (nee.has0) { A.sh_d0[s] = make_float4(nee.d0.x, nee.d0.y, nee.d0.z, nee.m0); A.sh_c0[s] = make_float4(nee.c0.x, nee.c0.y, nee.c0.z, 0.f); }
-                if (nee.has1) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
+                store_nee(A, s, nee);
                 if (!LF_SHADOW_FIRST) A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);   // else: A.thr, written below, is the same value
             } else if (surface) {
                 ps.rad = ps.rad + mk3(0.0f) * nee.T;              // radiance += DirectLight() * throughput with Li == 0 (pathtrace.glsl:266)
@@ -444,9 +453,7 @@ __global__ void __launch_bounds__(128, LF_FUSED_MINBLOCKS) k_shade_fused(DevScen
             const bool surface = shade_hit<COUNT, ENV, LIGHTS, TEX>(S, P, depth, ps, h, nee, sf, absnNext, cnt);
             wantShadow = nee.has0 || nee.has1;
             if (wantShadow) {
-                A.sh_o[s] = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, __int_as_float((nee.has0 ? 1 : 0) | (nee.has1 ? 2 : 0)));
-                if (nee.has0) { A.sh_d0[s] = make_float4(nee.d0.x, nee.d0.y, nee.d0.z, nee.m0); A.sh_c0[s] = make_float4(nee.c0.x, nee.c0.y, nee.c0.z, 0.f); }
-                if (nee.has1) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
+                store_nee(A, s, nee);
                 A.sh_T[s] = make_float4(nee.T.x, nee.T.y, nee.T.z, 0.f);
             } else if (surface) {
                 ps.rad = ps.rad + mk3(0.0f) * nee.T;              // radiance += DirectLight() * throughput with Li == 0 (pathtrace.glsl:266)
@@ -631,7 +638,7 @@ void launch_node_probe(cudaStream_t stream, const float4* nodes, unsigned num_no
 template <bool CULL, bool COUNT>
 static void launch_trace_kernels_s(const LaunchCtx& L, int which, const int* queue, const int* countp, int* cursor) {
     // the throughput of the NEE sum: PathSoA::thr while k_sample has not run yet, the copy in sh_T otherwise
-    const float4* neeT = (LF_SHADOW_FIRST && !shade_is_fused(L)) ? L.soa.thr : L.soa.sh_T;
+    const Pair<float4> neeT = (LF_SHADOW_FIRST && !shade_is_fused(L)) ? L.soa.thr : L.soa.sh_T;
     if (L.stack_depth <= 32) {
         if (which == 0) k_trace<false, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);
         else k_trace<true, CULL, COUNT, 32><<<L.persistent_blocks, kBlockThreads, 0, L.stream>>>(L.scene, L.soa, queue, countp, cursor, neeT, L.counters);

@@ -80,31 +80,39 @@ struct DevParams {
     int   preview, pv_w, pv_h, pv_y0, use_dof;
 };
 
-// Per-path state, structure of arrays; one slot = one pixel-sample of the batch.
+// Per-path state; one slot = one pixel-sample of the batch.  Every field is a 16-byte element, and fields that are read or written
+// TOGETHER share a 32-byte record (Pair: element i of a field lives at p[2 i]), i.e. one DRAM sector: after the first bounce the live
+// slots are scattered, and a 16-byte access to a plain array drags the dead neighbour's half of the sector along.
+template <class T>
+struct Pair {
+    T* p;
+    __host__ __device__ T& operator[](size_t i) const { return p[2 * i]; }
+};
 struct PathSoA {
-    float4* ray_o;     // origin.xyz
-    float4* ray_d;     // direction.xyz
-    float4* hit_f;     // t, bary u, bary v, emitter pdf
-    int4*   hit_i;     // triangle ref, instance, emitter light index (-1: surface), matID
-    float4* hit_p;     // first hit point (world), closest_hit.glsl:139,143
-    float4* thr;       // throughput.xyz, bsdfSampleRec.pdf
-    float4* rad;       // radiance.xyz
-    float4* absn;      // absorption.xyz
-    float4* stale;     // state.mat.emission of the last shaded surface (pathtrace.glsl:246-253 on emitter hits)
-    uint4*  rng;       // pcg4d state
+    Pair<float4> ray_o;     // origin.xyz                                                           } one record
+    Pair<float4> ray_d;     // direction.xyz                                                        }
+    Pair<float4> hit_f;     // t, bary u, bary v                                                    } one record
+    Pair<int4>   hit_i;     // triangle ref, instance, emitter light index (-1: surface), matID    }
+    Pair<float4> thr;       // throughput.xyz, bsdfSampleRec.pdf                                    } one record
+    Pair<float4> rad;       // radiance.xyz                                                         }
+    Pair<float4> absn;      // absorption.xyz                                                       } one record
+    Pair<float4> stale;     // state.mat.emission of the last shaded surface (pathtrace.glsl:246-253 on emitter hits; scenes with lights only)
+    Pair<uint4>  rng;       // pcg4d state                                                          } one record
+    Pair<float4> hit_p;     // first hit point (world), closest_hit.glsl:139,143 (paths that go on) }
     // what DisneySample needs of `State`, handed from the hit/NEE kernel to the sample kernel
-    float4* sf0;       // normal.xyz, eta
-    float4* sf1;       // albedo.xyz, specular
-    float4* sf2;       // metallic, roughness, specularTint, sheenTint
-    float4* sf3;       // sheen, clearcoat, clearcoatRoughness, specTrans
-    float4* sf4;       // -log(extinction)/atDistance .xyz, subsurface
-    // next-event estimation requests of the current bounce
-    float4* sh_o;      // surfacePos.xyz, number of candidate rays in .w bits
-    float4* sh_d0;     // env light direction.xyz, max distance
-    float4* sh_c0;     // env contribution (pathtrace.glsl:155)
-    float4* sh_d1;     // analytic light direction.xyz, max distance
-    float4* sh_c1;     // analytic light contribution (:197)
-    float4* sh_T;      // throughput the sum is multiplied with (:266)
+    Pair<float4> sf0;       // normal.xyz, eta                                                      } one record
+    Pair<float4> sf1;       // albedo.xyz, specular                                                 }
+    Pair<float4> sf2;       // metallic, roughness, specularTint, sheenTint                         } one record
+    Pair<float4> sf3;       // sheen, clearcoat, clearcoatRoughness, specTrans                      }
+    Pair<float4> sf4;       // -log(extinction)/atDistance .xyz, subsurface                         } one record
+    Pair<float4> sh_T;      // throughput the NEE sum is multiplied with (:266; fused kernel only)  }
+    // next-event estimation requests of the current bounce.  Candidate 0 is the environment ray when there is one, else the analytic
+    // light's; candidate 1 the analytic light's when both exist (so a request with one ray touches two records, not three)
+    Pair<float4> sh_o;      // surfacePos.xyz, candidate mask in .w bits (bit 0: candidate 0, bit 1: candidate 1)   } one record
+    Pair<float4> sh_d0;     // candidate 0: direction.xyz, max distance                                             }
+    Pair<float4> sh_c0;     // candidate 0: weighted contribution (pathtrace.glsl:155 / :197)       } one record
+    Pair<float4> sh_c1;     // candidate 1: contribution                                            }
+    float4* sh_d1;          // candidate 1: direction.xyz, max distance
 };
 
 struct Queues {

@@ -221,12 +221,25 @@ int alloc_state(lfcuda_ctx* ctx, int tile_w, int tile_h, int frames_req) {
     struct Arr { void** p; size_t elem; };
     PathSoA& S = ctx->soa;
     Queues& Q = ctx->queues;
-    std::vector<Arr> arrs = {
-        {(void**)&S.ray_o, 16}, {(void**)&S.ray_d, 16}, {(void**)&S.hit_f, 16}, {(void**)&S.hit_p, 16}, {(void**)&S.thr, 16}, {(void**)&S.rad, 16},
-        {(void**)&S.absn, 16}, {(void**)&S.stale, 16}, {(void**)&S.sf0, 16}, {(void**)&S.sf1, 16}, {(void**)&S.sf2, 16}, {(void**)&S.sf3, 16},
-        {(void**)&S.sf4, 16}, {(void**)&S.sh_o, 16}, {(void**)&S.sh_d0, 16}, {(void**)&S.sh_c0, 16}, {(void**)&S.sh_d1, 16}, {(void**)&S.sh_c1, 16},
-        {(void**)&S.sh_T, 16}, {(void**)&S.hit_i, 16}, {(void**)&S.rng, 16},
-        {(void**)&Q.active[0], 4}, {(void**)&Q.active[1], 4}, {(void**)&Q.shadow, 4}, {(void**)&Q.sample, 4},
+    // 32-byte records of two fields each (lf_types.h Pair) + the one plain float4 array + the queues
+    void* rec[10] = {};
+    std::vector<Arr> arrs;
+    for (void*& r : rec) arrs.push_back({&r, 32});
+    arrs.push_back({(void**)&S.sh_d1, 16});
+    arrs.push_back({(void**)&Q.active[0], 4}); arrs.push_back({(void**)&Q.active[1], 4});
+    arrs.push_back({(void**)&Q.shadow, 4}); arrs.push_back({(void**)&Q.sample, 4});
+    auto bind_records = [&]() {
+        auto lo = [&](int k) { return (float4*)rec[k]; };
+        S.ray_o.p = lo(0); S.ray_d.p = lo(0) + 1;
+        S.hit_f.p = lo(1); S.hit_i.p = (int4*)lo(1) + 1;
+        S.thr.p = lo(2); S.rad.p = lo(2) + 1;
+        S.absn.p = lo(3); S.stale.p = lo(3) + 1;
+        S.rng.p = (uint4*)lo(4); S.hit_p.p = lo(4) + 1;
+        S.sf0.p = lo(5); S.sf1.p = lo(5) + 1;
+        S.sf2.p = lo(6); S.sf3.p = lo(6) + 1;
+        S.sf4.p = lo(7); S.sh_T.p = lo(7) + 1;
+        S.sh_o.p = lo(8); S.sh_d0.p = lo(8) + 1;
+        S.sh_c0.p = lo(9); S.sh_c1.p = lo(9) + 1;
     };
     if (ctx->sort_rays) { arrs.push_back({(void**)&ctx->sort.sorted, 4}); arrs.push_back({(void**)&ctx->sort.keys, 4}); }
     size_t per_slot = 0;
@@ -253,7 +266,7 @@ int alloc_state(lfcuda_ctx* ctx, int tile_w, int tile_h, int frames_req) {
             e = cudaMalloc((void**)&ctx->sort.hist, (size_t)kSortBins * sizeof(unsigned));
             if (e == cudaSuccess) ctx->state_allocs.push_back(ctx->sort.hist);
         }
-        if (e == cudaSuccess) { ctx->capacity = cap; break; }
+        if (e == cudaSuccess) { bind_records(); ctx->capacity = cap; break; }
         free_state(ctx);
         cudaGetLastError();   // clear the sticky allocation error
         if (e != cudaErrorMemoryAllocation) return fail(ctx, LFCUDA_ECUDA, "path state allocation failed: %s", cudaGetErrorString(e));

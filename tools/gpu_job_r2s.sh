@@ -1,0 +1,16 @@
+# Round 2 (1 GPU): GPU suite, then the path state in 32-byte records of two fields each (one DRAM sector per pair) against the commit before.
+tag=${1:-r2s}
+out=gpurun_out
+mkdir -p $out
+( time timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 ) > $out/${tag}_pytest_gpu.txt 2>&1
+tail -4 $out/${tag}_pytest_gpu.txt
+ab() {
+  w=$1; name=$2; shift; shift
+  env "$@" timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-llvmpipe --no-c5 --workload $w > $out/${tag}_ab_${w}_$name.json 2> $out/${tag}_ab_${w}_$name.err
+  echo "== $w $name"; python tools/bench_brief.py < $out/${tag}_ab_${w}_$name.json | cut -c1-260
+}
+for w in c2_full c4_stress c3_full c1; do
+  ab $w default LF_DUMMY=1
+  ab $w prev LF_LFCUDA_SO=$PWD/ab/prev.so
+  ab $w default2 LF_DUMMY=2
+done
