@@ -280,6 +280,30 @@ int  lfcuda_measure_read_bandwidth(lfcuda_ctx* ctx, size_t bytes, int32_t iters,
  * wavefronts), measured in the run instead of read from a file. */
 int  lfcuda_measure_node_fetch(lfcuda_ctx* ctx, size_t table_bytes, int32_t iters, double* gbps_out);
 
+/* ---- bottom-level BVH build on the device (csrc/lf_blas.cu, csrc/lf_blas_build.h) ----------------
+ * The BVH of ONE mesh, node for node what the reference builds on the host at scene load: Mesh::BuildBVH (LavaFrame/Mesh.cpp:93-111) ->
+ * RadeonRays::SplitBvh(2.0f, 64, 0, 0.001f, 0)::Build (Mesh.h:18; thirdparty/RadeonRays/split_bvh.cpp:11-289: binned-SAH object splits - with
+ * max_split_depth 0 the spatial-split branch is never entered -, two-pointer partition, halving fallback, right child first), flattened in
+ * pre-order as BvhTranslator::ProcessBLASNodes does (bvh_translator.cpp:35-60).  No context is needed; the call is thread-safe.
+ *   prim_bounds   num_prims x 6 floats: pmin.xyz, pmax.xyz of every triangle (what Mesh::BuildBVH passes to Bvh::Build)
+ *   out_nodes     capacity (2 * num_prims - 1) x 9 words.  Node k: pmin.xyz, pmax.xyz (fp32) and three INT32: inner node = (left, right, 0)
+ *                 with left == k + 1; leaf = (startidx into out_indices, numprims 1..3, 1).  Node 0's box is Bvh::Bounds().
+ *   out_indices   num_prims primitive indices in leaf order (Bvh::GetIndices; Scene.cpp:196-209 forms vertIndices from them)
+ * info->negative_zero != 0: a bound is -0.0; the tree is still the reference's, but the SIGN of a zero box plane may differ from the host
+ * build's (std::min keeps the first of +0 / -0 it meets) - callers that need identical bytes take the host build for that mesh. */
+typedef struct LfBlasInfo {
+    int32_t num_nodes;       /* Bvh::m_nodecnt */
+    int32_t num_indices;     /* Bvh::GetNumIndices() == num_prims (no reference is duplicated without spatial splits) */
+    int32_t height;          /* Bvh::GetHeight() */
+    int32_t negative_zero;
+    int32_t levels;          /* height + 1 */
+    int32_t launches;        /* kernels launched */
+    float   build_ms;        /* device time of the build steps (CUDA events) */
+    float   total_ms;        /* wall time of the call: allocation, upload, build, read-back */
+} LfBlasInfo;
+int  lfcuda_build_blas(int32_t device, const float* prim_bounds, int32_t num_prims, float traversal_cost, int32_t num_bins,
+                       float* out_nodes, int32_t* out_indices, LfBlasInfo* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,11 @@ class LfStageStats(C.Structure):
         return {n: {"launches": int(self.launches[i]), "ms": float(self.ms[i])} for i, n in enumerate(STAGE_NAMES)}
 
 
+class LfBlasInfo(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("num_indices", C.c_int32), ("height", C.c_int32), ("negative_zero", C.c_int32),
+                ("levels", C.c_int32), ("launches", C.c_int32), ("build_ms", C.c_float), ("total_ms", C.c_float)]
+
+
 class LfCudaError(RuntimeError):
     pass
 
@@ -122,6 +127,7 @@ LFCUDA_SYMBOLS = {
     "lfcuda_get_stage_stats": (C.c_int, [C.c_void_p, C.POINTER(LfStageStats)]),
     "lfcuda_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "lfcuda_measure_read_bandwidth": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int32, C.POINTER(C.c_double)]),
+    "lfcuda_build_blas": (C.c_int, [C.c_int32, c_float_p, C.c_int32, C.c_float, C.c_int32, c_float_p, C.POINTER(C.c_int32), C.POINTER(LfBlasInfo)]),
 }
 
 _lfcuda = None
@@ -191,5 +197,44 @@ def load_lfhost():
     lib.lfhost_renderer_run.argtypes = [C.c_void_p, C.c_int]
     lib.lfhost_renderer_preview_hdr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lfhost_set_preview.argtypes = [C.c_float, C.c_int]
+    lib.lfhost_set_device_blas.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.lfhost_blas_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
+    lib.lfhost_reference_blas.argtypes = [c_float_p, C.c_int, c_float_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     _lfhost = lib
     return lib
+
+
+def build_blas(prim_bounds, device=0, traversal_cost=2.0, num_bins=64):
+    """lfcuda_build_blas on an [n, 6] float32 array of triangle boxes: (boxes [k, 6] float32, lr [k, 3] int32, indices [n] int32, info dict).
+    The arguments default to what Mesh.h:18 constructs: SplitBvh(2.0f, 64, 0, 0.001f, 0)."""
+    import numpy as np
+    lib = load_lfcuda()
+    b = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    n = b.shape[0]
+    nodes = np.zeros(9 * max(2 * n - 1, 1), np.float32)
+    idx = np.zeros(max(n, 1), np.int32)
+    info = LfBlasInfo()
+    rc = lib.lfcuda_build_blas(device, b.ctypes.data_as(c_float_p), n, traversal_cost, num_bins, nodes.ctypes.data_as(c_float_p),
+                               idx.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info))
+    if rc != 0:
+        raise LfCudaError(f"lfcuda_build_blas: {rc}: {lib.lfcuda_last_error(None).decode()}")
+    a = nodes[:9 * info.num_nodes].reshape(info.num_nodes, 9)
+    return a[:, :6].copy(), a[:, 6:].copy().view(np.int32), idx[:n], {f: getattr(info, f) for f, _ in LfBlasInfo._fields_}
+
+
+def reference_blas(prim_bounds):
+    """The reference's own builder (SplitBvh of the unchanged split_bvh.cpp inside liblfhost.so) on the same boxes, in build_blas' layout:
+    the ground truth of the BLAS tests.  CPU only; test support."""
+    import numpy as np
+    lib = load_lfhost()
+    b = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    n = b.shape[0]
+    nodes = np.zeros(9 * max(2 * n - 1, 1), np.float32)
+    idx = np.zeros(n, np.int32)
+    info = np.zeros(3, np.int32)
+    rc = lib.lfhost_reference_blas(b.ctypes.data_as(c_float_p), n, nodes.ctypes.data_as(c_float_p), idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   info.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise ValueError("lfhost_reference_blas failed")
+    a = nodes[:9 * int(info[0])].reshape(int(info[0]), 9)
+    return a[:, :6].copy(), a[:, 6:].copy().view(np.int32), idx, {"num_nodes": int(info[0]), "num_indices": int(info[1]), "height": int(info[2])}
