@@ -478,7 +478,7 @@ def main():
         "config": {"workload": desc, "resolution": [W, H], "spp_per_step": S, "spp_total": S * K * world, "full_config_spp": full_spp,
                    "max_depth": pt.params.max_depth, "parallelism": f"spp-split x{world}" if world > 1 else "single GPU",
                    "kernels": "megakernel" if args.kernel_mode == 1 else "wavefront",
-                   "l2_policy": "scene geometry (~165 MB) + 32 M-path state (~11 GB) exceed the 126 MB L2 every step; no flush needed"},
+                   "l2_policy": f"the path state one step touches ({S * W * H * 352 / 1e9:.1f} GB: spp_per_step x pixels x 352 B) and the scene geometry exceed the 126 MB L2 every step; no flush needed"},
         "mrays_per_s": mrays, "rays_per_sample": rays / max(1, c["samples"]),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
                 "path": ("lfcuda_set_params + lfcuda_set_camera + lfcuda_render_frames + lfcuda_read_accum (host buffers)" if world == 1 else

@@ -46,17 +46,18 @@ struct DevExec {
     }
 };
 
-struct Arena {                       // every device array of one build; freed together
-    std::vector<void*> ptrs;
-    cudaError_t err = cudaSuccess;
+struct Arena {                       // every device array of one build comes out of ONE allocation (a cudaMalloc / cudaFree pair costs more than a level)
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
     template <class T>
-    T* get(size_t count) {
-        void* p = nullptr;
-        if (err == cudaSuccess) err = cudaMalloc(&p, count * sizeof(T) + 16);
-        if (err == cudaSuccess) ptrs.push_back(p);
-        return (T*)p;
+    T* get(size_t count) {           // pass 1 (base == nullptr): sizes only
+        const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+        T* p = base ? (T*)(base + used) : nullptr;
+        used += bytes;
+        return p;
     }
-    ~Arena() { for (void* p : ptrs) cudaFree(p); }
+    cudaError_t commit() { cap = used; used = 0; return cudaMalloc((void**)&base, cap); }
+    ~Arena() { if (base) cudaFree(base); }
 };
 
 int blas_fail(int code, const char* what, cudaError_t e) {
@@ -92,19 +93,24 @@ extern "C" int lfcuda_build_blas(int32_t device, const float* prim_bounds, int32
         Arena A;
         State S{};
         S.n = n; S.nbins = num_bins; S.tc = traversal_cost;
-        float* d_in = A.get<float>(6 * (size_t)n);
-        S.in_bounds = d_in;
-        for (int k = 0; k < 2; k++) { S.lo[k] = A.get<float4>(n); S.hi[k] = A.get<float4>(n); S.node_of[k] = A.get<int>(n); S.lev[k] = A.get<LevelNode>(lcap); }
-        S.flag = A.get<int>((size_t)n + 1); S.scan = A.get<int>((size_t)n + 1); S.chunk = A.get<int>(chunk_capacity(n));
-        S.pairL = A.get<int>(n); S.pairR = A.get<int>(n);
-        S.nflag = A.get<int>(lcap); S.nscan = A.get<int>(lcap);
-        S.g = A.get<GNode>(2 * (size_t)n);
-        S.bin_cap = lcap < 65536 ? lcap : 65536;                       // 5 376 bytes of bins per inner node; wider levels go in batches
-        S.bins = A.get<float>((size_t)S.bin_cap * 3 * kBinFields * kMaxBins);
-        S.misc = A.get<int>(4);
-        S.out_nodes = A.get<float>(9 * 2 * (size_t)n);
-        S.out_indices = A.get<int>(n);
-        if (A.err != cudaSuccess) rc = blas_fail(A.err == cudaErrorMemoryAllocation ? LFCUDA_ENOMEM : LFCUDA_ECUDA, "device allocation", A.err);
+        float* d_in = nullptr;
+        cudaError_t ea = cudaSuccess;
+        for (int pass = 0; pass < 2 && ea == cudaSuccess; pass++) {       // sizes, then pointers
+            d_in = A.get<float>(6 * (size_t)n);
+            S.in_bounds = d_in;
+            for (int k = 0; k < 2; k++) { S.lo[k] = A.get<float4>(n); S.hi[k] = A.get<float4>(n); S.node_of[k] = A.get<int>(n); S.lev[k] = A.get<LevelNode>(lcap); }
+            S.flag = A.get<int>((size_t)n + 1); S.scan = A.get<int>((size_t)n + 1); S.chunk = A.get<int>(chunk_capacity(n));
+            S.pairL = A.get<int>(n); S.pairR = A.get<int>(n);
+            S.nflag = A.get<int>(lcap); S.nscan = A.get<int>(lcap);
+            S.g = A.get<GNode>(2 * (size_t)n);
+            S.bin_cap = lcap < 65536 ? lcap : 65536;                       // 5 376 bytes of bins per inner node; wider levels go in batches
+            S.bins = A.get<float>((size_t)S.bin_cap * 3 * kBinFields * kMaxBins);
+            S.misc = A.get<int>(4);
+            S.out_nodes = A.get<float>(9 * 2 * (size_t)n);
+            S.out_indices = A.get<int>(n);
+            if (pass == 0) ea = A.commit();
+        }
+        if (ea != cudaSuccess) rc = blas_fail(ea == cudaErrorMemoryAllocation ? LFCUDA_ENOMEM : LFCUDA_ECUDA, "device allocation", ea);
         if (!rc && (e = cudaMemcpyAsync(d_in, prim_bounds, 6 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, stream)) != cudaSuccess)
             rc = blas_fail(LFCUDA_ECUDA, "upload of the primitive bounds", e);
         if (!rc) {

@@ -43,7 +43,7 @@ namespace blas {
 
 constexpr int kMaxBins = 64;
 constexpr int kBinFields = 7;        // count, pmin.xyz, pmax.xyz
-constexpr int kScanChunk = 1024;     // elements one work item of the prefix sum handles sequentially
+constexpr int kScanChunk = 32;       // elements one work item of the prefix sum handles sequentially
 
 struct Box { float mn[3], mx[3]; };
 BB_HD float smin(float a, float b) { return (b < a) ? b : a; }     // std::min(a, b)
@@ -97,7 +97,26 @@ BB_HD void acc_or(int* a, int v) {
     *a |= v;
 #endif
 }
-BB_HD void acc_box(Box* dst, const Box& b) { for (int k = 0; k < 3; k++) { acc_min(&dst->mn[k], b.mn[k]); acc_max(&dst->mx[k], b.mx[k]); } }
+#ifdef __CUDA_ARCH__
+BB_HD int ordered_int(float f) { if (f == 0.f) f = 0.f; const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }    // monotonic float -> int
+BB_HD float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+#endif
+BB_HD void acc_box(Box* dst, const Box& b) {
+#ifdef __CUDA_ARCH__
+    // the lanes of a warp that grow the same box (near the root: all of them) reduce among themselves first: one atomic per group and plane
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, (unsigned long long)dst);
+    if (__popc(peers) >= 4) {
+        const bool leader = (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1);
+        for (int k = 0; k < 3; k++) {
+            const int lo = __reduce_min_sync(peers, ordered_int(b.mn[k])), hi = __reduce_max_sync(peers, ordered_int(b.mx[k]));
+            if (leader) { acc_min(&dst->mn[k], ordered_float(lo)); acc_max(&dst->mx[k], ordered_float(hi)); }
+        }
+        return;
+    }
+#endif
+    for (int k = 0; k < 3; k++) { acc_min(&dst->mn[k], b.mn[k]); acc_max(&dst->mx[k], b.mx[k]); }
+}
 
 // ---- one node of the level being split (Bvh::SplitRequest + the decisions taken for it)
 struct LevelNode {
@@ -110,6 +129,7 @@ struct LevelNode {
     int nL, split;           // elements of the left class; first position of the right child
     int allL, allR;          // the partition ran and left a side empty: that side's grown boxes are kept (split_bvh.cpp:145-160)
     int moved;               // 1 = elements change places
+    int sidx[3]; float sahv[3];  // best plane of every axis and its cost (StepSahAxis)
     Box b, cb;               // bounds, centroid bounds
 };
 struct GNode {               // node store
@@ -138,7 +158,9 @@ struct State {
     float* out_nodes;                   // num_nodes x 9 words: pmin, pmax, then three INT32: (left, right, 0) / (startidx, numprims, 1)
     int* out_indices;                   // n: packed primitive indices (Bvh::GetIndices)
 };
-BB_HD float* bin_field(const State& S, int slot, int axis, int field) { return S.bins + (((size_t)slot * 3 + axis) * kBinFields + field) * kMaxBins; }
+// bins[axis][field][bin][slot]: the slot (= inner node of the level) is the fastest index, so that the SAH sweeps of neighbouring nodes, one
+// work item each, read neighbouring words
+BB_HD float* bin_at(const State& S, int slot, int axis, int field, int bin) { return S.bins + ((((size_t)axis * kBinFields + field) * kMaxBins + bin) * (size_t)S.bin_cap + slot); }
 BB_HD Box ref_box(const float4& lo, const float4& hi) { Box b; b.mn[0] = lo.x; b.mn[1] = lo.y; b.mn[2] = lo.z; b.mx[0] = hi.x; b.mx[1] = hi.y; b.mx[2] = hi.z; return b; }
 BB_HD int f2i(float f) { union { float f; int i; } u; u.f = f; return u.i; }
 BB_HD float i2f(int i) { union { float f; int i; } u; u.i = i; return u.f; }
@@ -202,8 +224,9 @@ struct StepRank {        // after the prefix sum over nflag; misc[1] = inner nod
 struct StepBinsClear {
     State S; int nslots;
     BB_HD void operator()(int i) const {
-        const int field = (i / kMaxBins) % kBinFields;
-        S.bins[i] = field == 0 ? i2f(0) : (field <= 3 ? FLT_MAX : -FLT_MAX);
+        const int slot = i % nslots, r = i / nslots;          // r = (axis * kBinFields + field) * kMaxBins + bin
+        const int field = (r / kMaxBins) % kBinFields;
+        S.bins[(size_t)r * S.bin_cap + slot] = field == 0 ? i2f(0) : (field <= 3 ? FLT_MAX : -FLT_MAX);
     }
 };
 // Histogram of the primitive references over the centroid box, per axis (split_bvh.cpp:214-232)
@@ -226,53 +249,65 @@ struct StepBin {
             const float lim = (float)(S.nbins - 1);
             const int bin = (int)((lim < x) ? lim : x);                       // (int)std::min<float>(x, lim)
             const int slot = nd.rank - rank_lo;
-            acc_add((int*)bin_field(S, slot, axis, 0) + bin, 1);
-            for (int k = 0; k < 3; k++) { acc_min(bin_field(S, slot, axis, 1 + k) + bin, b.mn[k]); acc_max(bin_field(S, slot, axis, 4 + k) + bin, b.mx[k]); }
+            acc_add((int*)bin_at(S, slot, axis, 0, bin), 1);
+            for (int k = 0; k < 3; k++) { acc_min(bin_at(S, slot, axis, 1 + k, bin), b.mn[k]); acc_max(bin_at(S, slot, axis, 4 + k, bin), b.mx[k]); }
         }
     }
 };
-// FindObjectSahSplit (split_bvh.cpp:170-289) and the choice of plane in BuildNode (split_bvh.cpp:59-98,108), one work item per inner node
-struct StepSah {
+// FindObjectSahSplit (split_bvh.cpp:170-289), one work item per (inner node, axis): the cheapest of the axis' 63 planes, first one on ties.
+// The reference carries ONE running minimum through the three axes (strict `<`), i.e. it keeps the first minimum in (axis, plane) order;
+// the first minimum of every axis, combined in axis order with the same strict `<` (StepSahPick), is the same plane.
+struct StepSahAxis {
+    State S; int cur, rank_lo, rank_hi;
+    BB_HD void operator()(int i) const {
+        const int j = i / 3, a = i - 3 * j;
+        LevelNode& nd = S.lev[cur][j];
+        if (nd.rank < rank_lo || nd.rank >= rank_hi) return;
+        const int slot = nd.rank - rank_lo, nb = S.nbins;
+        nd.sidx[a] = -1; nd.sahv[a] = FLT_MAX;
+        const float cext[3] = {nd.cb.mx[0] - nd.cb.mn[0], nd.cb.mx[1] - nd.cb.mn[1], nd.cb.mx[2] - nd.cb.mn[2]};
+        if ((cext[0] * cext[0] + cext[1] * cext[1]) + cext[2] * cext[2] == 0.f) return;      // split_bvh.cpp:186-190
+        if (cext[a] == 0.f) return;                                                          // :212
+        const float invarea = 1.f / box_area(nd.b);
+        float rsa[kMaxBins];                                                                 // surface areas of rightbounds[i]
+        Box rb; box_clear(rb);
+#pragma unroll 4
+        for (int k = nb - 1; k > 0; --k) {
+            Box bb; for (int c = 0; c < 3; c++) { bb.mn[c] = *bin_at(S, slot, a, 1 + c, k); bb.mx[c] = *bin_at(S, slot, a, 4 + c, k); }
+            box_grow(rb, bb);
+            rsa[k - 1] = box_area(rb);
+        }
+        Box lb; box_clear(lb);
+        int leftcount = 0, rightcount = nd.count, splitidx = -1;
+        float sah = FLT_MAX;
+#pragma unroll 4
+        for (int k = 0; k < nb - 1; ++k) {
+            Box bb; for (int c = 0; c < 3; c++) { bb.mn[c] = *bin_at(S, slot, a, 1 + c, k); bb.mx[c] = *bin_at(S, slot, a, 4 + c, k); }
+            box_grow(lb, bb);
+            const int cnt = f2i(*bin_at(S, slot, a, 0, k));
+            leftcount += cnt;
+            rightcount -= cnt;
+            const float sahtmp = S.tc + ((float)leftcount * box_area(lb) + (float)rightcount * rsa[k]) * invarea;
+            if (sahtmp < sah) { splitidx = k; sah = sahtmp; }
+        }
+        nd.sidx[a] = splitidx; nd.sahv[a] = sah;
+    }
+};
+// ... and the choice of plane in BuildNode (split_bvh.cpp:59-98,108), one work item per inner node
+struct StepSahPick {
     State S; int cur, rank_lo, rank_hi;
     BB_HD void operator()(int j) const {
         LevelNode& nd = S.lev[cur][j];
         if (nd.rank < rank_lo || nd.rank >= rank_hi) return;
-        const int slot = nd.rank - rank_lo, nb = S.nbins;
         int axis = box_maxdim(nd.cb);
         float border = center_of(nd.cb.mn[axis], nd.cb.mx[axis]);
-        // ---- FindObjectSahSplit
         int splitidx = -1, dim = 0;
         float sah = FLT_MAX;
+        for (int a = 0; a < 3; a++)
+            if (nd.sidx[a] != -1 && nd.sahv[a] < sah) { dim = a; splitidx = nd.sidx[a]; sah = nd.sahv[a]; }
         float split = i2f(0x7fc00000);
-        const float cext[3] = {nd.cb.mx[0] - nd.cb.mn[0], nd.cb.mx[1] - nd.cb.mn[1], nd.cb.mx[2] - nd.cb.mn[2]};
-        if (!((cext[0] * cext[0] + cext[1] * cext[1]) + cext[2] * cext[2] == 0.f)) {
-            const float invarea = 1.f / box_area(nd.b);
-            for (int a = 0; a < 3; a++) {
-                if (cext[a] == 0.f) continue;
-                const int* cnt = (const int*)bin_field(S, slot, a, 0);
-                const float* f[6];
-                for (int k = 0; k < 6; k++) f[k] = bin_field(S, slot, a, 1 + k);
-                float rsa[kMaxBins];                                             // surface areas of rightbounds[i]
-                Box rb; box_clear(rb);
-                for (int i = nb - 1; i > 0; --i) {
-                    Box bb; for (int k = 0; k < 3; k++) { bb.mn[k] = f[k][i]; bb.mx[k] = f[3 + k][i]; }
-                    box_grow(rb, bb);
-                    rsa[i - 1] = box_area(rb);
-                }
-                Box lb; box_clear(lb);
-                int leftcount = 0, rightcount = nd.count;
-                for (int i = 0; i < nb - 1; ++i) {
-                    Box bb; for (int k = 0; k < 3; k++) { bb.mn[k] = f[k][i]; bb.mx[k] = f[3 + k][i]; }
-                    box_grow(lb, bb);
-                    leftcount += cnt[i];
-                    rightcount -= cnt[i];
-                    const float sahtmp = S.tc + ((float)leftcount * box_area(lb) + (float)rightcount * rsa[i]) * invarea;
-                    if (sahtmp < sah) { dim = a; splitidx = i; sah = sahtmp; }
-                }
-            }
-            if (splitidx != -1) split = nd.cb.mn[dim] + (float)(splitidx + 1) * (cext[dim] / (float)nb);
-        }
-        // ---- BuildNode: max_split_depth = 0, the object split or the centre of the centroid box
+        if (splitidx != -1) split = nd.cb.mn[dim] + (float)(splitidx + 1) * ((nd.cb.mx[dim] - nd.cb.mn[dim]) / (float)S.nbins);
+        // max_split_depth = 0: the object split, or the centre of the centroid box when there is none
         if (!is_nan(split)) { border = split; axis = dim; }
         nd.axis = axis; nd.border = border;
         nd.near2far = (nd.count + nd.start) & 1;
@@ -381,39 +416,37 @@ struct StepEmit {
         else { oi[0] = S.g[g.left].pre; oi[1] = S.g[g.right].pre; oi[2] = 0; }
     }
 };
-// ---- exclusive prefix sum of n ints in three steps (chunk sums, serial scan of the sums, chunk-local scans)
+// ---- exclusive prefix sum of n ints: sums of chunks of 32, the sums scanned the same way (recursively, in place), chunk-local scans.
+// Integer sums: exact whatever the grouping.  `in == out` is allowed (a work item reads an element before it overwrites it).
 struct StepScanSum {
-    const int* in; int* chunk; int n;
+    const int* in; int* sums; int n;
     BB_HD void operator()(int c) const {
         int s = 0; const int e = (c + 1) * kScanChunk < n ? (c + 1) * kScanChunk : n;
         for (int i = c * kScanChunk; i < e; i++) s += in[i];
-        chunk[c] = s;
+        sums[c] = s;
     }
 };
-struct StepScanTop {
-    int* chunk; int nchunks;
-    BB_HD void operator()(int) const { int s = 0; for (int c = 0; c < nchunks; c++) { int v = chunk[c]; chunk[c] = s; s += v; } chunk[nchunks] = s; }
-};
 struct StepScanWrite {
-    const int* in; int* out; const int* chunk; int n;
+    const int* in; int* out; const int* sums; int n;      // sums: exclusive prefix of the chunk sums (nullptr: a single chunk)
     BB_HD void operator()(int c) const {
-        int s = chunk[c]; const int e = (c + 1) * kScanChunk < n ? (c + 1) * kScanChunk : n;
-        for (int i = c * kScanChunk; i < e; i++) { out[i] = s; s += in[i]; }
+        int s = sums ? sums[c] : 0; const int e = (c + 1) * kScanChunk < n ? (c + 1) * kScanChunk : n;
+        for (int i = c * kScanChunk; i < e; i++) { const int v = in[i]; out[i] = s; s += v; }
     }
 };
 template <class Exec>
-void exclusive_scan(Exec& ex, const int* in, int* out, int* chunk, int n) {
+void exclusive_scan(Exec& ex, const int* in, int* out, int* scratch, int n) {
     const int nchunks = (n + kScanChunk - 1) / kScanChunk;
-    ex.run(nchunks, StepScanSum{in, chunk, n});
-    ex.run(1, StepScanTop{chunk, nchunks});
-    ex.run(nchunks, StepScanWrite{in, out, chunk, n});
+    if (nchunks <= 1) { ex.run(1, StepScanWrite{in, out, nullptr, n}); return; }
+    ex.run(nchunks, StepScanSum{in, scratch, n});
+    exclusive_scan(ex, scratch, scratch, scratch + nchunks, nchunks);
+    ex.run(nchunks, StepScanWrite{in, out, scratch, n});
 }
 
 struct Result { int num_nodes, height, negative_zero, levels; };
 
 // Storage a build of n primitives needs (bytes per array), for the executors' allocators
 inline int level_capacity(int n) { return n / 2 + 2; }         // an inner node holds >= 4 references, so a level has <= 2 * (n / 4) nodes
-inline int chunk_capacity(int n) { return (n + 1 + kScanChunk - 1) / kScanChunk + 2; }
+inline int chunk_capacity(int n) { return (n + 1) / (kScanChunk - 1) + 64; }     // all levels of the recursive prefix sum
 
 // The level loop.  Exec: run(count, step) executes step(0..count-1) in any order / in parallel, with a barrier between runs;
 // read_int(ptr) reads one int the steps wrote.
@@ -435,7 +468,8 @@ Result build(Exec& ex, State& S) {
             const int hi = lo + S.bin_cap < ninner ? lo + S.bin_cap : ninner;
             ex.run((hi - lo) * 3 * kBinFields * kMaxBins, StepBinsClear{S, hi - lo});
             ex.run(S.n, StepBin{S, cur, lo, hi});
-            ex.run(ncur, StepSah{S, cur, lo, hi});
+            ex.run(3 * ncur, StepSahAxis{S, cur, lo, hi});
+            ex.run(ncur, StepSahPick{S, cur, lo, hi});
         }
         ex.run(S.n + 1, StepFlag{S, cur});
         exclusive_scan(ex, S.flag, S.scan, S.chunk, S.n + 1);

@@ -351,12 +351,19 @@ LFD bool walk_leaf(const DevScene& S, const Walk& w, float maxDist, Hit& hit, De
         // two non-zero floats of strictly opposite sign is negative, so those cases are rejected from the sign of the
         // product, before any division; everything else takes the shader's exact arithmetic.
         float a = dot(tv, pv);
+#ifdef LF_TRI_BRANCHLESS   // experiment: one combined sign test after all three products (same values, no early exits)
+        f3 qv = cross(tv, e0);
+        float b = dot(w.d, qv);
+        float c = dot(e1, qv);
+        if (a * det < 0.f || b * det < 0.f || c * det < 0.f) continue;
+#else
         if (a * det < 0.f) continue;
         f3 qv = cross(tv, e0);
         float b = dot(w.d, qv);
         if (b * det < 0.f) continue;
         float c = dot(e1, qv);
         if (c * det < 0.f) continue;
+#endif
         float rdet = 1.0f / det;                  // uvt.xyz / det = uvt.xyz * rcp(det)
         float uu = a * rdet;
         float vv = b * rdet;

@@ -203,9 +203,11 @@ int ensure_counts(lfcuda_ctx* ctx, int max_depth) {
     return 0;
 }
 
-constexpr size_t kAutoSlots = (size_t)32 << 20;   // auto batch: about 32 M pixel-samples in flight.  Measured on C2: 4 M -> 328, 8 M -> 360,
+constexpr size_t kAutoSlots = (size_t)64 << 20;   // auto batch: about 64 M pixel-samples in flight (24 GB of the 180).  Measured on C2: 4 M -> 328, 8 M -> 360,
                                                   // 16 M -> 377 M samples/s with the first kernels, 16 M -> 427, 32 M -> 435, 64 M -> 436 with
-                                                  // the final ones: deep bounces keep enough rays to fill the persistent grid.
+                                                  // later ones: deep bounces keep enough rays to fill the persistent grid.  A 4K frame is 8.3 M slots:
+                                                  // 32 M gave C4 batches of 3 frames; 8 / 16 / 32 frames per batch measured +1.0 / +1.4 / +1.5 %
+                                                  // (profiles/r2/r2u_ab_c4_stress_fif*.json), so the default went to 64 M (7 frames of 4K).
 
 // Path state for tiles of tile_w x tile_h pixels, `frames_req` frames per batch (0 = auto).  The auto batch is clamped to half of the
 // device memory that is free right now, and an allocation failure retries with half the frames (a GPU shared with torch / NCCL buffers

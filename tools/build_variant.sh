@@ -10,8 +10,10 @@ nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=${LF_FMAD:-fals
      -Iinclude -Ilavaframe_b200/csrc "$@" -c lavaframe_b200/csrc/lf_kernels.cu -o build/ab/$name.kernels.o
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -std=c++17 \
      -Iinclude -Ilavaframe_b200/csrc -c lavaframe_b200/csrc/lf_tlas.cu -o build/ab/$name.tlas.o
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -std=c++17 \
+     -Iinclude -Ilavaframe_b200/csrc -c lavaframe_b200/csrc/lf_blas.cu -o build/ab/$name.blas.o
 g++ -O2 -fPIC -std=c++17 -ffp-contract=off -Iinclude -Ilavaframe_b200/csrc -I/usr/local/cuda/include $defs -c lavaframe_b200/csrc/lfcuda.cpp -o build/ab/$name.lfcuda.o
 g++ -O2 -fPIC -std=c++17 -ffp-contract=off -Iinclude -Ilavaframe_b200/csrc -I/usr/local/cuda/include $defs -c lavaframe_b200/csrc/lf_repack.cpp -o build/ab/$name.repack.o
 g++ -O2 -fPIC -std=c++17 -ffp-contract=off -Iinclude -Ilavaframe_b200/csrc -I/usr/local/cuda/include $defs -c lavaframe_b200/csrc/lfcuda_group.cpp -o build/ab/$name.group.o
-g++ -shared -o ab/$name.so build/ab/$name.kernels.o build/ab/$name.lfcuda.o build/ab/$name.repack.o build/ab/$name.group.o build/ab/$name.tlas.o -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+g++ -shared -o ab/$name.so build/ab/$name.kernels.o build/ab/$name.lfcuda.o build/ab/$name.repack.o build/ab/$name.group.o build/ab/$name.tlas.o build/ab/$name.blas.o -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built ab/$name.so"
