@@ -289,8 +289,9 @@ int  lfcuda_measure_node_fetch(lfcuda_ctx* ctx, size_t table_bytes, int32_t iter
  *   out_nodes     capacity (2 * num_prims - 1) x 9 words.  Node k: pmin.xyz, pmax.xyz (fp32) and three INT32: inner node = (left, right, 0)
  *                 with left == k + 1; leaf = (startidx into out_indices, numprims 1..3, 1).  Node 0's box is Bvh::Bounds().
  *   out_indices   num_prims primitive indices in leaf order (Bvh::GetIndices; Scene.cpp:196-209 forms vertIndices from them)
- * info->negative_zero != 0: a bound is -0.0; the tree is still the reference's, but the SIGN of a zero box plane may differ from the host
- * build's (std::min keeps the first of +0 / -0 it meets) - callers that need identical bytes take the host build for that mesh. */
+ * Identical means identical bits, the sign of a zero box plane included: std::min / std::max keep the first of +0 / -0 they meet, so that sign
+ * depends on the order in which the reference grows a box; the order is restated (lf_blas_build.h, acc_zero).  info->negative_zero only reports
+ * that some bound is -0.0. */
 typedef struct LfBlasInfo {
     int32_t num_nodes;       /* Bvh::m_nodecnt */
     int32_t num_indices;     /* Bvh::GetNumIndices() == num_prims (no reference is duplicated without spatial splits) */

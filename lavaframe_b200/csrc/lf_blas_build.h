@@ -14,8 +14,10 @@
 //
 // This file restates that builder as level-synchronous data-parallel steps whose results do not depend on the order in which the items of
 // a step run, and which produce the reference's tree NODE FOR NODE:
-//   * min / max / counts are exact and order-independent (the sign of a zero aside: std::min keeps the first of +0 / -0; a mesh that contains a
-//     -0.0 coordinate is reported through `negative_zero` so that the caller can take the host build instead of risking a differing sign bit);
+//   * min / max / counts are exact and order-independent - the sign of a zero aside: std::min / std::max keep the FIRST of +0 / -0 they meet, so a
+//     box plane that is exactly zero carries the sign of the first zero in the reference's growth order.  That order is restated as a key per
+//     element (array index for the root, destination position for a left child, (block, position) for a right child, see acc_zero) and the
+//     smallest key among a plane's zeros decides the sign; no decision of the builder looks at it, only the node boxes it writes out;
 //   * the SAH sweep of a node is the reference's sequential fp32 code, run literally by one work item per node;
 //   * the two-pointer partition is determined by the L / R classes alone: the elements in place stay, the k-th misplaced element from the left
 //     (an R in the first nL positions) is exchanged with the misplaced L that has k L's after it; positions follow from a prefix sum.
@@ -63,6 +65,7 @@ BB_HD int box_maxdim(const Box& b) {                                            
 }
 BB_HD float center_of(float mn, float mx) { return (mx + mn) * 0.5f; }                                                   // bbox::center, bbox.cpp:28
 BB_HD bool is_nan(float v) { return v != v; }
+BB_HD unsigned f2i_bits(float f) { union { float f; unsigned u; } c; c.f = f; return c.u; }
 
 // ---- order-independent accumulation.  Device: atomics (float min / max through the integer order of IEEE floats); host executor: plain.
 BB_HD void acc_min(float* a, float v) {
@@ -118,6 +121,13 @@ BB_HD void acc_box(Box* dst, const Box& b) {
     for (int k = 0; k < 3; k++) { acc_min(&dst->mn[k], b.mn[k]); acc_max(&dst->mx[k], b.mx[k]); }
 }
 
+BB_HD void acc_min64(unsigned long long* a, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    atomicMin(a, v);
+#else
+    if (v < *a) *a = v;
+#endif
+}
 // ---- one node of the level being split (Bvh::SplitRequest + the decisions taken for it)
 struct LevelNode {
     int start, count;        // range of primitive references
@@ -130,6 +140,7 @@ struct LevelNode {
     int allL, allR;          // the partition ran and left a side empty: that side's grown boxes are kept (split_bvh.cpp:145-160)
     int moved;               // 1 = elements change places
     int sidx[3]; float sahv[3];  // best plane of every axis and its cost (StepSahAxis)
+    unsigned long long zkey[6];  // per plane of b: (growth order << 1 | sign bit) of the first zero-valued contribution (acc_zero)
     Box b, cb;               // bounds, centroid bounds
 };
 struct GNode {               // node store
@@ -138,6 +149,21 @@ struct GNode {               // node store
     int leaf;
     int size, pre;           // nodes of the subtree; pre-order position
 };
+
+// The sign of zero planes (see the header).  `order` = the element's place in the sequence in which the reference grows this box.
+BB_HD void zkey_clear(LevelNode& nd) { for (int k = 0; k < 6; k++) nd.zkey[k] = ~0ull; }
+BB_HD void acc_zero(LevelNode* nd, const Box& b, unsigned long long order) {
+    for (int k = 0; k < 3; k++) {
+        if (b.mn[k] == 0.f) acc_min64(&nd->zkey[k], (order << 1) | (unsigned long long)(f2i_bits(b.mn[k]) >> 31));
+        if (b.mx[k] == 0.f) acc_min64(&nd->zkey[3 + k], (order << 1) | (unsigned long long)(f2i_bits(b.mx[k]) >> 31));
+    }
+}
+BB_HD void zero_signs(Box& b, const LevelNode& nd) {
+    for (int k = 0; k < 3; k++) {
+        if (b.mn[k] == 0.f) b.mn[k] = (nd.zkey[k] & 1ull) ? -0.f : 0.f;
+        if (b.mx[k] == 0.f) b.mx[k] = (nd.zkey[3 + k] & 1ull) ? -0.f : 0.f;
+    }
+}
 
 struct State {
     int n, nbins;
@@ -154,7 +180,7 @@ struct State {
     GNode* g;                           // 2 n - 1
     float* bins;                        // bin_cap x 3 x kBinFields x kMaxBins (counts stored as int bits)
     int bin_cap;
-    int* misc;                          // [0] a primitive bound is -0.0, [1] inner nodes of the current level
+    int* misc;                          // [0] a primitive bound is -0.0 (reported, nothing depends on it), [1] inner nodes of the current level
     float* out_nodes;                   // num_nodes x 9 words: pmin, pmax, then three INT32: (left, right, 0) / (startidx, numprims, 1)
     int* out_indices;                   // n: packed primitive indices (Bvh::GetIndices)
 };
@@ -181,6 +207,7 @@ struct StepInit {
         Box c; for (int k = 0; k < 3; k++) c.mn[k] = c.mx[k] = center_of(b.mn[k], b.mx[k]);
         acc_box(&S.lev[0][0].b, b);
         acc_box(&S.lev[0][0].cb, c);
+        acc_zero(&S.lev[0][0], b, (unsigned long long)i);                     // Bvh::Build grows m_bounds in index order (bvh.cpp:43-47)
     }
 };
 struct StepRoot {        // before StepInit
@@ -188,7 +215,7 @@ struct StepRoot {        // before StepInit
     BB_HD void operator()(int) const {
         LevelNode& r = S.lev[0][0];
         r.start = 0; r.count = S.n; r.gid = 0; r.rank = -1;
-        box_clear(r.b); box_clear(r.cb);
+        box_clear(r.b); box_clear(r.cb); zkey_clear(r);
         S.misc[0] = 0;
     }
 };
@@ -200,6 +227,7 @@ struct StepClassify {
         LevelNode& nd = S.lev[cur][j];
         GNode& g = S.g[nd.gid];
         g.b = nd.b;
+        zero_signs(g.b, nd);
         const bool leaf = nd.count < 4;
         S.nflag[j] = leaf ? 0 : 1;
         g.leaf = leaf ? 1 : 0;
@@ -351,7 +379,7 @@ struct StepSplit {
         LevelNode& r = S.lev[cur ^ 1][2 * nd.rank + 1];
         l.start = nd.start; l.count = nd.split - nd.start; l.gid = g.left; l.rank = -1;
         r.start = nd.split; r.count = nd.count - l.count; r.gid = g.right; r.rank = -1;
-        box_clear(l.b); box_clear(l.cb); box_clear(r.b); box_clear(r.cb);
+        box_clear(l.b); box_clear(l.cb); box_clear(r.b); box_clear(r.cb); zkey_clear(l); zkey_clear(r);
     }
 };
 // Where the misplaced elements are (see the header: the two-pointer partition exchanges them pairwise, split_bvh.cpp:113-137)
@@ -390,6 +418,25 @@ struct StepMove {
         // the halving fallback re-grows the boxes by position on top of what the partition loop put into them: everything, on the side all went to
         if (!right || nd.allL) { acc_box(&ch[0].b, b); acc_box(&ch[0].cb, c); }
         if (right || nd.allR) { acc_box(&ch[1].b, b); acc_box(&ch[1].cb, c); }
+        // Growth order of the two boxes (only the sign of a zero plane depends on it).  Left: the first pointer passes the elements in place in
+        // ascending position and a misplaced left-class element joins when it is swapped in, i.e. ascending DESTINATION.  Right, when the loop
+        // runs to a split (or finds no left-class element at all): the element the first pointer stops at, then the elements in place above
+        // it in DESCENDING position down to the next misplaced one, and so on: blocks numbered by the left-class elements above, each block's
+        // lowest destination first.  Fresh boxes of the halving fallback (split_bvh.cpp:145-160) grow in ascending position.
+        const bool hasZero = b.mn[0] == 0.f || b.mn[1] == 0.f || b.mn[2] == 0.f || b.mx[0] == 0.f || b.mx[1] == 0.f || b.mx[2] == 0.f;
+        if (hasZero) {
+            if (!right || nd.allL) acc_zero(&ch[0], b, (unsigned long long)q);
+            if (right || nd.allR) {
+                unsigned long long order = (unsigned long long)q;
+                if (nd.moved || nd.allR) {
+                    const int loopsplit = nd.moved ? nd.split : nd.start;
+                    const unsigned long long block = (unsigned long long)(nd.nL - (S.scan[q + 1] - S.scan[nd.start]));     // left-class elements above q
+                    const bool first = S.flag[q] != 0 || q == loopsplit;
+                    order = (block << 31) | (first ? 0ull : (unsigned long long)(0x7fffffff - q));
+                }
+                acc_zero(&ch[1], b, order);
+            }
+        }
     }
 };
 // ---- flattening (BvhTranslator::ProcessBLASNodes, bvh_translator.cpp:35-60): subtree sizes bottom-up, pre-order positions top-down

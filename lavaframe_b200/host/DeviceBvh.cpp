@@ -55,7 +55,6 @@ void LfDeviceSplitBvh::BuildImpl(bbox const* bounds, int numbounds) {
     }
     // spatial splits (max_split_depth > 0) are not what Mesh.h:18 asks for and not what the device builder restates; tiny meshes are not worth a launch
     const bool on_device = enable && split_depth_ <= 0 && numbounds >= min_prims && numbounds >= 1;
-    bool fallback_zero = false;
     if (on_device) {
         std::vector<float> nodes(9 * (size_t)(2 * (size_t)numbounds));
         std::vector<int32_t> indices(numbounds);
@@ -63,8 +62,7 @@ void LfDeviceSplitBvh::BuildImpl(bbox const* bounds, int numbounds) {
         const int rc = lfcuda_build_blas(device, reinterpret_cast<const float*>(bounds), numbounds, cost_, bins_, nodes.data(), indices.data(), &info);
         if (rc != 0)   // asked for and impossible: say so, do not quietly build elsewhere
             throw std::runtime_error(std::string("LfDeviceSplitBvh: device BLAS build failed: ") + lfcuda_last_error(nullptr));
-        if (info.negative_zero) fallback_zero = true;     // a -0.0 bound: the host build alone guarantees the same sign bits (lfcuda.h)
-        else {
+        {
             m_nodes.assign(info.num_nodes, Node{});
             for (int k = 0; k < info.num_nodes; k++) {
                 const float* r = &nodes[9 * (size_t)k];
@@ -80,7 +78,7 @@ void LfDeviceSplitBvh::BuildImpl(bbox const* bounds, int numbounds) {
             m_packed_indices.assign(indices.begin(), indices.end());
             m_height = info.height;
             std::lock_guard<std::mutex> lock(g.m);
-            g.stats.device_builds++; g.stats.device_ms += info.build_ms; g.stats.device_total_ms += info.total_ms; g.stats.device_prims += numbounds;
+            g.stats.device_builds++; g.stats.negative_zero_meshes += info.negative_zero ? 1 : 0; g.stats.device_ms += info.build_ms; g.stats.device_total_ms += info.total_ms; g.stats.device_prims += numbounds;
             return;
         }
     }
@@ -89,7 +87,6 @@ void LfDeviceSplitBvh::BuildImpl(bbox const* bounds, int numbounds) {
     const double dt = now_ms() - t0;
     std::lock_guard<std::mutex> lock(g.m);
     g.stats.host_builds++; g.stats.host_ms += dt; g.stats.host_prims += numbounds;
-    if (fallback_zero) g.stats.negative_zero_fallbacks++;
 }
 
 }  // namespace RadeonRays

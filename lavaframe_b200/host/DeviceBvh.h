@@ -31,7 +31,7 @@ private:
 }  // namespace RadeonRays
 
 namespace lfhost {
-struct BlasStats { int device_builds, host_builds, negative_zero_fallbacks; double device_ms, device_total_ms, host_ms; long long device_prims, host_prims; };
+struct BlasStats { int device_builds, host_builds, negative_zero_meshes; double device_ms, device_total_ms, host_ms; long long device_prims, host_prims; };
 void SetDeviceBlas(int enable, int min_prims, int device);     // enable < 0: leave as is (environment: LF_DEVICE_BLAS, LF_DEVICE_BLAS_MIN)
 BlasStats GetBlasStats(bool reset);
 }  // namespace lfhost

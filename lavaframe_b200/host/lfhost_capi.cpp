@@ -72,10 +72,10 @@ int lfhost_reference_blas(const float* prim_bounds, int n, float* out_nodes, int
 // Mesh BVHs built on the GPU (DeviceBvh.h) for the scenes loaded from now on: enable 0 / 1 (-1: keep), meshes below min_prims triangles stay on
 // the host (-1: keep), CUDA device (-1: keep).  Off by default: north_star keeps the reference's host build as the source of the node arrays.
 void lfhost_set_device_blas(int enable, int min_prims, int device) { lfhost::SetDeviceBlas(enable, min_prims, device); }
-// out[8]: device builds, host builds, -0.0 fallbacks, device triangles, host triangles, device ms (kernels), device ms (whole calls), host ms
+// out[8]: device builds, host builds, device-built meshes with a -0.0 bound, device triangles, host triangles, device ms (kernels), device ms (whole calls), host ms
 void lfhost_blas_stats(double* out, int reset) {
     lfhost::BlasStats s = lfhost::GetBlasStats(reset != 0);
-    out[0] = s.device_builds; out[1] = s.host_builds; out[2] = s.negative_zero_fallbacks; out[3] = (double)s.device_prims; out[4] = (double)s.host_prims;
+    out[0] = s.device_builds; out[1] = s.host_builds; out[2] = s.negative_zero_meshes; out[3] = (double)s.device_prims; out[4] = (double)s.host_prims;
     out[5] = s.device_ms; out[6] = s.device_total_ms; out[7] = s.host_ms;
 }
 

@@ -70,3 +70,19 @@ def synthetic_cases():
     grid = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(8), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
     cases.append(("regular_grid", boxes(grid, np.full((len(grid), 3), 0.5))))
     return cases
+
+
+def signed_zero_cases():
+    """Boxes on a coarse integer grid whose zero coordinates carry random signs: the builder's decisions never look at the sign of a zero, but the
+    boxes it writes out do (std::min / std::max keep the first of +0 / -0 they meet, in the order the reference grows a box)."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for n, span in ((5, 1), (9, 1), (40, 2), (300, 2), (300, 1), (2500, 3), (20000, 4), (4000, 0)):
+        for rep in range(3):
+            lo = rng.integers(-span, span + 1, (n, 3)).astype(np.float32)
+            hi = lo + rng.integers(0, 2, (n, 3)).astype(np.float32)
+            b = np.concatenate([lo, hi], axis=1).astype(np.float32)
+            z = b == 0
+            b[z & (rng.random(b.shape) < 0.5)] = -0.0
+            cases.append((f"signed_zero_n{n}_span{span}_{rep}", b))
+    return cases

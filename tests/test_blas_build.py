@@ -13,7 +13,7 @@ import pytest
 
 import lavaframe_b200 as lf
 from lavaframe_b200.capi import lib_path, reference_blas
-from blas_cases import pack_meshes, split_nodes, synthetic_cases
+from blas_cases import pack_meshes, split_nodes, synthetic_cases, signed_zero_cases
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
@@ -66,6 +66,20 @@ def test_text_against_the_reference_builder(hostbuild, order):
         got = hostbuild(b, order=order, bin_cap=(5 if order == 2 else 4096))
         assert_same_tree(got, rb, rl, ri, f"{name} order {order}")
         assert got[3]["height"] == rinfo["height"], name
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_sign_of_zero_planes(hostbuild, order):
+    """Boxes full of +0 / -0 coordinates: the node boxes carry the sign the reference's growth order gives them, bit for bit, in any execution order."""
+    if not os.path.exists(lib_path("liblfhost.so")):
+        pytest.skip("liblfhost.so not built (needs /root/reference at build time)")
+    planes = 0
+    for name, b in signed_zero_cases():
+        rb, rl, ri, rinfo = reference_blas(b)
+        got = hostbuild(b, order=order, bin_cap=64)
+        assert_same_tree(got, rb, rl, ri, f"{name} order {order}")
+        planes += int((np.signbit(rb) & (rb == 0)).sum())
+    assert planes > 10000          # the cases do exercise it: that many box planes of the reference's trees are -0.0
 
 
 def test_negative_zero_is_reported(hostbuild):

@@ -12,7 +12,7 @@ import pytest
 
 import lavaframe_b200 as lf
 from lavaframe_b200.capi import lib_path, reference_blas
-from blas_cases import pack_meshes, synthetic_cases
+from blas_cases import pack_meshes, synthetic_cases, signed_zero_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -41,6 +41,17 @@ def test_device_build_against_the_reference_builder(gpu):
         got = lf.build_blas(b, gpu)
         assert_same_tree(got, rb, rl, ri, name)
         assert got[3]["height"] == rinfo["height"], name
+
+
+def test_device_build_sign_of_zero_planes(gpu):
+    """+0 / -0 coordinates: the sign of every zero box plane is the one the reference's growth order gives it (lf_blas_build.h acc_zero)."""
+    if not os.path.exists(lib_path("liblfhost.so")):
+        pytest.fail("liblfhost.so missing: __graft_entry__.build() must run where /root/reference exists")
+    for name, b in signed_zero_cases():
+        rb, rl, ri, rinfo = reference_blas(b)
+        got = lf.build_blas(b, gpu)
+        assert_same_tree(got, rb, rl, ri, name)
+        assert got[3]["negative_zero"] == int((np.signbit(b) & (b == 0)).any())
 
 
 def test_device_build_is_repeatable_and_reports_negative_zero(gpu):
