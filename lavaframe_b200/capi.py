@@ -199,7 +199,6 @@ def load_lfhost():
     lib.lfhost_set_preview.argtypes = [C.c_float, C.c_int]
     lib.lfhost_set_device_blas.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.lfhost_blas_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
-    lib.lfhost_reference_blas.argtypes = [c_float_p, C.c_int, c_float_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     _lfhost = lib
     return lib
 
@@ -221,20 +220,3 @@ def build_blas(prim_bounds, device=0, traversal_cost=2.0, num_bins=64):
     a = nodes[:9 * info.num_nodes].reshape(info.num_nodes, 9)
     return a[:, :6].copy(), a[:, 6:].copy().view(np.int32), idx[:n], {f: getattr(info, f) for f, _ in LfBlasInfo._fields_}
 
-
-def reference_blas(prim_bounds):
-    """The reference's own builder (SplitBvh of the unchanged split_bvh.cpp inside liblfhost.so) on the same boxes, in build_blas' layout:
-    the ground truth of the BLAS tests.  CPU only; test support."""
-    import numpy as np
-    lib = load_lfhost()
-    b = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
-    n = b.shape[0]
-    nodes = np.zeros(9 * max(2 * n - 1, 1), np.float32)
-    idx = np.zeros(n, np.int32)
-    info = np.zeros(3, np.int32)
-    rc = lib.lfhost_reference_blas(b.ctypes.data_as(c_float_p), n, nodes.ctypes.data_as(c_float_p), idx.ctypes.data_as(C.POINTER(C.c_int32)),
-                                   info.ctypes.data_as(C.POINTER(C.c_int32)))
-    if rc != 0:
-        raise ValueError("lfhost_reference_blas failed")
-    a = nodes[:9 * int(info[0])].reshape(int(info[0]), 9)
-    return a[:, :6].copy(), a[:, 6:].copy().view(np.int32), idx, {"num_nodes": int(info[0]), "num_indices": int(info[1]), "height": int(info[2])}

@@ -18,26 +18,6 @@ extern LavaFrameState GlobalState;
 
 static int quiet_log(const char*, ...) { return 0; }
 
-// The REFERENCE's mesh BVH builder (the unchanged split_bvh.cpp linked into this library) run on a caller's boxes and flattened in
-// BvhTranslator::ProcessBLASNodes' pre-order (bvh_translator.cpp:35-60): the ground truth the tests hold lfcuda_build_blas against.
-namespace {
-struct RefBlasProbe : RadeonRays::SplitBvh {
-    RefBlasProbe() : RadeonRays::SplitBvh(2.0f, 64, 0, 0.001f, 0) {}      // Mesh.h:18
-    int cur = 0;
-    int Emit(const Node* nd, float* out) {
-        const int k = cur++;
-        float* r = out + 9 * (size_t)k;
-        r[0] = nd->bounds.pmin.x; r[1] = nd->bounds.pmin.y; r[2] = nd->bounds.pmin.z;
-        r[3] = nd->bounds.pmax.x; r[4] = nd->bounds.pmax.y; r[5] = nd->bounds.pmax.z;
-        int32_t* ri = reinterpret_cast<int32_t*>(r + 6);
-        if (nd->type == kLeaf) { ri[0] = nd->startidx; ri[1] = nd->numprims; ri[2] = 1; }
-        else { ri[2] = 0; ri[0] = Emit(nd->lc, out); ri[1] = Emit(nd->rc, out); }
-        return k;
-    }
-    int Flatten(float* out) { cur = 0; Emit(m_root, out); return (int)m_nodecnt; }
-};
-}  // namespace
-
 extern "C" {
 
 // LoadSceneFromFile + `scene->renderOptions = renderOptions` exactly as Main.cpp:961-969 does, with the linear
@@ -56,18 +36,6 @@ void* lfhost_load_scene(const char* path, int keep_tonemap, int verbose) {
     return scene;
 }
 void lfhost_free_scene(void* s) { delete static_cast<Scene*>(s); }
-
-// Test support: out_nodes (2 n - 1) x 9 words and out_indices n in lfcuda_build_blas' layout; info = {nodes, indices, height}
-int lfhost_reference_blas(const float* prim_bounds, int n, float* out_nodes, int32_t* out_indices, int32_t* info) {
-    if (n < 1) return -1;
-    RefBlasProbe bvh;
-    bvh.Build(reinterpret_cast<const RadeonRays::bbox*>(prim_bounds), n);
-    info[0] = bvh.Flatten(out_nodes);
-    info[1] = (int32_t)bvh.GetNumIndices();
-    info[2] = bvh.GetHeight();
-    memcpy(out_indices, bvh.GetIndices(), sizeof(int32_t) * bvh.GetNumIndices());
-    return 0;
-}
 
 // Mesh BVHs built on the GPU (DeviceBvh.h) for the scenes loaded from now on: enable 0 / 1 (-1: keep), meshes below min_prims triangles stay on
 // the host (-1: keep), CUDA device (-1: keep).  Off by default: north_star keeps the reference's host build as the source of the node arrays.

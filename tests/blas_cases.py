@@ -4,7 +4,33 @@ A pack holds what Scene::CreateAccelerationStructures left (LavaFrame/Scene.cpp:
 RadeonRays::SplitBvh on the host (Mesh.cpp:93-111) and laid out by BvhTranslator::ProcessBLAS (bvh_translator.cpp:91-114), the triangle
 references in BVH leaf order and the meshes' vertices.  From these: the triangle boxes Mesh::BuildBVH fed the builder, and the tree and index
 order it produced - the ground truth for the device build and for its host-compiled text."""
+import ctypes as C
+import os
+
 import numpy as np
+
+REFBVH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "liblfrefbvh.so")
+
+
+def have_reference_builder():
+    return os.path.exists(REFBVH)
+
+
+def reference_blas(prim_bounds):
+    """The reference's own builder (RadeonRays::SplitBvh of the unchanged split_bvh.cpp, compiled into oracle/_ref/liblfrefbvh.so by
+    oracle/Makefile) on the same boxes, in lfcuda_build_blas' layout: (boxes [k, 6], lr [k, 3] int32, indices [n], info).  Test infrastructure."""
+    lib = C.CDLL(REFBVH)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    lib.lfref_build_blas.argtypes = [fp, C.c_int, fp, ip, ip]
+    b = np.ascontiguousarray(prim_bounds, dtype=np.float32).reshape(-1, 6)
+    n = b.shape[0]
+    nodes = np.zeros(9 * max(2 * n - 1, 1), np.float32)
+    idx = np.zeros(n, np.int32)
+    info = np.zeros(3, np.int32)
+    if lib.lfref_build_blas(b.ctypes.data_as(fp), n, nodes.ctypes.data_as(fp), idx.ctypes.data_as(ip), info.ctypes.data_as(ip)) != 0:
+        raise ValueError("lfref_build_blas failed")
+    a = nodes[:9 * int(info[0])].reshape(int(info[0]), 9)
+    return a[:, :6].copy(), a[:, 6:].copy().view(np.int32), idx, {"num_nodes": int(info[0]), "num_indices": int(info[1]), "height": int(info[2])}
 
 
 def pack_meshes(pack):

@@ -2,7 +2,7 @@
 level-synchronous data-parallel restatement of RadeonRays::SplitBvh (Mesh.h:18, split_bvh.cpp:11-289) must produce the reference builder's
 tree node for node, whatever the order in which the work items of a step run.  Ground truth: (1) the node arrays and triangle order inside
 the committed scene packs, which the reference's unchanged builder produced (tests/golden/*.lfpack), and (2) the reference's
-builder itself (the unchanged split_bvh.cpp inside liblfhost.so) run on synthetic and degenerate inputs.  The CUDA execution of the same text
+builder itself (the unchanged split_bvh.cpp, compiled into oracle/_ref/liblfrefbvh.so) run on synthetic and degenerate inputs.  The CUDA execution of the same text
 is tested in test_blas_device_gpu.py; nothing here is a product path."""
 import ctypes as C
 import os
@@ -12,8 +12,8 @@ import numpy as np
 import pytest
 
 import lavaframe_b200 as lf
-from lavaframe_b200.capi import lib_path, reference_blas
-from blas_cases import pack_meshes, split_nodes, synthetic_cases, signed_zero_cases
+from lavaframe_b200.capi import lib_path
+from blas_cases import pack_meshes, split_nodes, synthetic_cases, signed_zero_cases, reference_blas, have_reference_builder
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
@@ -59,8 +59,8 @@ def test_text_rebuilds_the_packs_trees(hostbuild, golden_dir, pack_name, order):
 
 @pytest.mark.parametrize("order", [0, 1, 2])
 def test_text_against_the_reference_builder(hostbuild, order):
-    if not os.path.exists(lib_path("liblfhost.so")):
-        pytest.skip("liblfhost.so not built (needs /root/reference at build time)")
+    if not have_reference_builder():
+        pytest.skip("oracle/_ref/liblfrefbvh.so not built (make -C oracle ref needs /root/reference)")
     for name, b in synthetic_cases():
         rb, rl, ri, rinfo = reference_blas(b)
         got = hostbuild(b, order=order, bin_cap=(5 if order == 2 else 4096))
@@ -71,8 +71,8 @@ def test_text_against_the_reference_builder(hostbuild, order):
 @pytest.mark.parametrize("order", [0, 1, 2])
 def test_sign_of_zero_planes(hostbuild, order):
     """Boxes full of +0 / -0 coordinates: the node boxes carry the sign the reference's growth order gives them, bit for bit, in any execution order."""
-    if not os.path.exists(lib_path("liblfhost.so")):
-        pytest.skip("liblfhost.so not built (needs /root/reference at build time)")
+    if not have_reference_builder():
+        pytest.skip("oracle/_ref/liblfrefbvh.so not built (make -C oracle ref needs /root/reference)")
     planes = 0
     for name, b in signed_zero_cases():
         rb, rl, ri, rinfo = reference_blas(b)

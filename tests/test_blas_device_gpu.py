@@ -11,8 +11,8 @@ import numpy as np
 import pytest
 
 import lavaframe_b200 as lf
-from lavaframe_b200.capi import lib_path, reference_blas
-from blas_cases import pack_meshes, synthetic_cases, signed_zero_cases
+from lavaframe_b200.capi import lib_path
+from blas_cases import pack_meshes, synthetic_cases, signed_zero_cases, reference_blas, have_reference_builder
 
 pytestmark = pytest.mark.gpu
 
@@ -34,8 +34,8 @@ def test_device_build_equals_the_packs_trees(gpu, golden_dir, pack_name):
 
 
 def test_device_build_against_the_reference_builder(gpu):
-    if not os.path.exists(lib_path("liblfhost.so")):
-        pytest.fail("liblfhost.so missing: __graft_entry__.build() must run where /root/reference exists")
+    if not have_reference_builder():
+        pytest.fail("oracle/_ref/liblfrefbvh.so missing: __graft_entry__.build() must run where /root/reference exists")
     for name, b in synthetic_cases():
         rb, rl, ri, rinfo = reference_blas(b)
         got = lf.build_blas(b, gpu)
@@ -45,8 +45,8 @@ def test_device_build_against_the_reference_builder(gpu):
 
 def test_device_build_sign_of_zero_planes(gpu):
     """+0 / -0 coordinates: the sign of every zero box plane is the one the reference's growth order gives it (lf_blas_build.h acc_zero)."""
-    if not os.path.exists(lib_path("liblfhost.so")):
-        pytest.fail("liblfhost.so missing: __graft_entry__.build() must run where /root/reference exists")
+    if not have_reference_builder():
+        pytest.fail("oracle/_ref/liblfrefbvh.so missing: __graft_entry__.build() must run where /root/reference exists")
     for name, b in signed_zero_cases():
         rb, rl, ri, rinfo = reference_blas(b)
         got = lf.build_blas(b, gpu)
