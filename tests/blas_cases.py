@@ -49,7 +49,12 @@ def pack_meshes(pack):
         leaf = sub[:, 8] == 1
         ntri = int(sub[leaf, 7].sum())
         v = verts[3 * tri_base:3 * (tri_base + ntri), :3].reshape(ntri, 3, 3)
-        bounds = np.concatenate([v.min(axis=1), v.max(axis=1)], axis=1).astype(np.float32)
+        # Mesh::BuildBVH grows the box by v1, v2, v3 with std::min / std::max, which keep the first of +0 / -0 (Mesh.cpp:101-107)
+        lo, hi = v[:, 0].copy(), v[:, 0].copy()
+        for k in (1, 2):
+            lo = np.where(v[:, k] < lo, v[:, k], lo)
+            hi = np.where(hi < v[:, k], v[:, k], hi)
+        bounds = np.concatenate([lo, hi], axis=1).astype(np.float32)
         idx = ((vi[tri_base:tri_base + ntri, 0] - 3 * tri_base) // 3).astype(np.int32)
         lr = np.zeros((end - root, 3), np.int32)
         lr[~leaf, 0] = sub[~leaf, 6].astype(np.int64) - root
@@ -112,3 +117,28 @@ def signed_zero_cases():
             b[z & (rng.random(b.shape) < 0.5)] = -0.0
             cases.append((f"signed_zero_n{n}_span{span}_{rep}", b))
     return cases
+
+
+def negative_zero_scene(outdir):
+    """c2_mini with a band of its bumpy sphere collapsed onto the coordinate planes, written the way OBJ exporters write such vertices:
+    `-0.0` for about half of them, `0.0` for the rest.  Returns the .scene path."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from scenes import gen_scenes
+    scene = gen_scenes.c2_mini(str(outdir))
+    obj = os.path.join(os.path.dirname(scene), "c2mini_mesh.obj")
+    rng = np.random.default_rng(3)
+    out, snapped = [], 0
+    for line in open(obj):
+        if line.startswith("v "):
+            y = []
+            for c in (float(t) for t in line.split()[1:4]):
+                if abs(c) < 0.12:
+                    c = -0.0 if rng.random() < 0.5 else 0.0
+                    snapped += 1
+                y.append(c)
+            line = "v %r %r %r\n" % tuple(y)
+        out.append(line)
+    open(obj, "w").write("".join(out))
+    assert snapped > 100
+    return scene

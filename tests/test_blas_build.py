@@ -13,7 +13,7 @@ import pytest
 
 import lavaframe_b200 as lf
 from lavaframe_b200.capi import lib_path
-from blas_cases import pack_meshes, split_nodes, synthetic_cases, signed_zero_cases, reference_blas, have_reference_builder
+from blas_cases import pack_meshes, split_nodes, synthetic_cases, signed_zero_cases, reference_blas, have_reference_builder, negative_zero_scene
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
@@ -80,6 +80,27 @@ def test_sign_of_zero_planes(hostbuild, order):
         assert_same_tree(got, rb, rl, ri, f"{name} order {order}")
         planes += int((np.signbit(rb) & (rb == 0)).sum())
     assert planes > 10000          # the cases do exercise it: that many box planes of the reference's trees are -0.0
+
+
+def test_loader_mesh_with_negative_zero_vertices(hostbuild, tmp_path):
+    """A mesh whose OBJ holds `-0.0` and `0.0` vertices, loaded and built by the reference's unchanged loader and builder (lf_scenepack): the
+    text rebuilds its tree with the same sign on every zero box plane."""
+    exe = os.path.join(os.path.dirname(lib_path("liblfcuda.so")), "bin", "lf_scenepack")
+    if not os.path.exists(exe):
+        pytest.skip("lf_scenepack not built (needs /root/reference at build time)")
+    try:
+        scene = negative_zero_scene(tmp_path)
+    except Exception as e:   # no reference assets available
+        pytest.skip(str(e))
+    pack_path = str(tmp_path / "nz.lfpack")
+    subprocess.run([exe, scene, pack_path], check=True, capture_output=True, env=dict(os.environ, LF_DEVICE_BLAS="0"))
+    pack = lf.ScenePack(pack_path)
+    nodes = pack.nodes.reshape(-1, 9)[:pack.top_index, :6]
+    assert int((np.signbit(nodes) & (nodes == 0)).sum()) > 500
+    for order in (0, 1, 2):
+        for k, m in enumerate(pack_meshes(pack)):
+            got = hostbuild(m["bounds"], order=order)
+            assert_same_tree(got, m["boxes"], m["lr"], m["indices"], f"mesh {k} order {order}")
 
 
 def test_negative_zero_is_reported(hostbuild):

@@ -12,7 +12,7 @@ import pytest
 
 import lavaframe_b200 as lf
 from lavaframe_b200.capi import lib_path
-from blas_cases import pack_meshes, synthetic_cases, signed_zero_cases, reference_blas, have_reference_builder
+from blas_cases import pack_meshes, synthetic_cases, signed_zero_cases, reference_blas, have_reference_builder, negative_zero_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -132,3 +132,21 @@ def test_renderer_on_a_device_built_scene(gpu, tmp_path):
         r.close(); s.close()
     lib.lfhost_set_device_blas(0, -1, -1)
     assert imgs[0].tobytes() == imgs[1].tobytes()
+
+
+def test_drop_in_pack_with_negative_zero_coordinates(gpu, tmp_path):
+    """An OBJ the way exporters write them - `-0.000000` for what rounds to zero, next to `0.000000`: the device-built scene is still the
+    host-built scene byte for byte (the sign of zero box planes follows the reference's growth order, lf_blas_build.h acc_zero)."""
+    import re
+    if not os.path.exists(lib_path("liblfhost.so")):
+        pytest.fail("liblfhost.so missing: __graft_entry__.build() must run where /root/reference exists")
+    scene = negative_zero_scene(tmp_path)
+    host_pack, dev_pack = str(tmp_path / "host.lfpack"), str(tmp_path / "dev.lfpack")
+    run_scenepack(scene, host_pack, {"LF_DEVICE_BLAS": "0"})
+    log_d = run_scenepack(scene, dev_pack, {"LF_DEVICE_BLAS": "1", "LF_DEVICE_BLAS_MIN": "1"})
+    m = re.search(r"(\d+) with -0.0 bounds", log_d)
+    assert m and int(m.group(1)) >= 1, log_d
+    a, b = open(host_pack, "rb").read(), open(dev_pack, "rb").read()
+    assert a == b
+    nodes = lf.ScenePack(host_pack).nodes.reshape(-1, 9)[:, :6]
+    assert int((np.signbit(nodes) & (nodes == 0)).sum()) > 0          # the reference's own node boxes do contain -0.0 planes here
