@@ -1,6 +1,8 @@
 // lfhost_capi.cpp — extern "C" handles over the C++ host side (the reference's Scene/Loader, unchanged, and
 // CudaRenderer) so that the Python tests and bench.py can drive the real drop-in class through ctypes.
+#include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -29,7 +31,12 @@ void* lfhost_load_scene(const char* path, int keep_tonemap, int verbose) {
     if (!keep_tonemap) ro.tonemapIndex = 0;
     Scene* scene = new Scene();
     GlobalState.scene = scene;
-    if (!LoadSceneFromFile(path, scene, ro)) { delete scene; return nullptr; }
+    bool ok = false;
+    try { ok = LoadSceneFromFile(path, scene, ro); }
+    catch (const std::exception& e) {   // a device BLAS build that was asked for and failed (DeviceBvh.cpp) must not unwind through the C boundary
+        fprintf(stderr, "lfhost_load_scene: %s\n", e.what());
+    }
+    if (!ok) { delete scene; return nullptr; }
     if (!keep_tonemap) ro.tonemapIndex = 0;
     scene->renderOptions = ro;
     scene->camera->isMoving = false;   // never initialised by Camera's ctor (Camera.cpp:101-117)

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -93,7 +94,10 @@ int main(int argc, char** argv) {
     ro.useVignette = false; ro.vignetteIntensity = 0.f; ro.vignettePower = 1.f;
     if (!keepTonemap) ro.tonemapIndex = 0;
     GlobalState.scene = new Scene();
-    if (!LoadSceneFromFile(argv[1], GlobalState.scene, ro)) return 1;
+    bool loaded = false;
+    try { loaded = LoadSceneFromFile(argv[1], GlobalState.scene, ro); }
+    catch (const std::exception& e) { fprintf(stderr, "lf_render: %s\n", e.what()); }         // LF_DEVICE_BLAS=1 without a usable GPU
+    if (!loaded) return 1;
     if (!keepTonemap) ro.tonemapIndex = 0;
     GlobalState.scene->renderOptions = ro;
     GlobalState.scene->camera->isMoving = false;

@@ -5,6 +5,7 @@
 //   lf_scenepack <scene file> <out.lfpack> [--info]
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 
 #include "Scene.h"
@@ -33,7 +34,10 @@ int main(int argc, char** argv) {
     ro.vignettePower = 1.f;
     Scene* scene = new Scene();
     GlobalState.scene = scene;
-    if (!LoadSceneFromFile(argv[1], scene, ro)) {
+    bool loaded = false;
+    try { loaded = LoadSceneFromFile(argv[1], scene, ro); }
+    catch (const std::exception& e) { fprintf(stderr, "lf_scenepack: %s\n", e.what()); }      // LF_DEVICE_BLAS=1 without a usable GPU
+    if (!loaded) {
         fprintf(stderr, "lf_scenepack: cannot load %s\n", argv[1]);
         return 1;
     }

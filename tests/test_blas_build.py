@@ -120,3 +120,22 @@ def test_leaf_order_is_right_child_first(hostbuild):
     assert sorted(idx.tolist()) == list(range(8)) and leaves[:, 1].sum() == 8
     assert leaves[0, 0] + leaves[0, 1] == 8          # pre-order's first leaf = the array's head = the last indices handed out
     assert (np.diff(leaves[:, 0]) < 0).all()
+
+
+def test_requested_device_build_fails_loudly_without_a_gpu(tmp_path):
+    """LF_DEVICE_BLAS=1 on a machine without a CUDA device: the loader reports the failure - it does not quietly fall back to the host build."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = os.path.join(os.path.dirname(lib_path("liblfcuda.so")), "bin", "lf_scenepack")
+    if not os.path.exists(exe):
+        pytest.skip("lf_scenepack not built (needs /root/reference at build time)")
+    from scenes import gen_scenes
+    try:
+        scene = gen_scenes.cornell_256(str(tmp_path))
+    except Exception as e:   # no reference assets available
+        pytest.skip(str(e))
+    r = subprocess.run([exe, scene, str(tmp_path / "x.lfpack")], capture_output=True, text=True, env=dict(os.environ, LF_DEVICE_BLAS="1", LF_DEVICE_BLAS_MIN="1"))
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and not os.path.exists(tmp_path / "x.lfpack")
+    with pytest.raises(lf.LfCudaError, match="no CUDA device"):
+        lf.build_blas(np.zeros((4, 6), np.float32), 0)
