@@ -78,6 +78,9 @@ extern "C" int lfcuda_build_blas(int32_t device, const float* prim_bounds, int32
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return blas_fail(LFCUDA_ECUDA, "no CUDA device available; liblfcuda has no CPU fallback", e);
     if (device < 0 || device >= ndev) return blas_fail(LFCUDA_EINVAL, "device out of range", cudaSuccess);
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);                                   // the caller's current device is put back before returning
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device};
     if ((e = cudaSetDevice(device)) != cudaSuccess) return blas_fail(LFCUDA_ECUDA, "cudaSetDevice", e);
     const auto t0 = std::chrono::steady_clock::now();
     int sms = 0;
