@@ -72,6 +72,8 @@ LFD void load_path(const DevScene& S, const PathSoA& A, int s, int depth, PathRe
     ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab);
     ps.stale = LIGHTS ? xyz(A.stale[s]) : mk3(0.f);
 }
+// A material whose albedo or metallic / roughness come (partly) from a texture (pathtrace.glsl:82-91; the conditions of load_surface)
+LFD bool material_is_textured(const DevScene& S, float texA, float texMR) { return S.num_tex > 0 && ((int)texA >= 0 || (int)texMR >= 0); }
 // The shadow request of a surface hit.  A single candidate always goes into slot 0 of the request, whichever kind it is (with one ray the
 // order of the sum Li = 0 + c is the same), so that the common request touches two 32-byte records; with both, the environment ray is 0.
 LFD void store_nee(const PathSoA& A, int s, const Nee& nee) {
@@ -359,13 +361,23 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
                 A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
                 if (LIGHTS) A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
                 A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
-                A.hit_p[s] = make_float4(h.fhp.x, h.fhp.y, h.fhp.z, 0.f);                   // k_sample starts the next ray from it
                 const Mat& m = sf.mat;
                 A.sf0[s] = make_float4(sf.normal.x, sf.normal.y, sf.normal.z, sf.eta);
+#if LF_SAMPLE_REMAT
+                // k_sample starts the next ray from the hit point and re-reads the material `h.mat` from the table; what a texture changed
+                // of it travels with the path
+                A.hit_p[s] = make_float4(h.fhp.x, h.fhp.y, h.fhp.z, __int_as_float(h.mat));
+                if (TEX && material_is_textured(S, m.texA, m.texMR)) {
+                    A.sf1[s] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.specular);
+                    A.sf2[s] = make_float4(m.metallic, m.roughness, m.specularTint, m.sheenTint);
+                }
+#else
+                A.hit_p[s] = make_float4(h.fhp.x, h.fhp.y, h.fhp.z, 0.f);                   // k_sample starts the next ray from it
                 A.sf1[s] = make_float4(m.albedo.x, m.albedo.y, m.albedo.z, m.specular);
                 A.sf2[s] = make_float4(m.metallic, m.roughness, m.specularTint, m.sheenTint);
                 A.sf3[s] = make_float4(m.sheen, m.clearcoat, m.clearcoatRoughness, m.specTrans);
                 A.sf4[s] = make_float4(absnNext.x, absnNext.y, absnNext.z, m.subsurface);
+#endif
             }
         }
         queue_push(Q.sample, sampleCount, wantSample, s);
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
 #ifndef LF_SAMPLE_MINBLOCKS
 #define LF_SAMPLE_MINBLOCKS 6   // ms of k_sample per 6 C2 steps: 6 CTAs per SM 26.3, 8: 30.4 (profiles/r2/r2d_ab_c2_full_shade4s6.json)
 #endif
-__global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P, PathSoA A, Queues Q, int depth) {
+__global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevScene S, DevParams P, PathSoA A, Queues Q, int depth) {
     const int count = Q.counts[4 * Q.stride + depth];
     int* next = (depth & 1) ? Q.active[0] : Q.active[1];
     int* nextCount = Q.counts + 0 * Q.stride + depth + 1;
@@ -389,8 +401,25 @@ __global__ void __launch_bounds__(128, LF_SAMPLE_MINBLOCKS) k_sample(DevParams P
             s = Q.sample[i];
             PathRegs ps;
             float4 d = A.ray_d[s], th = A.thr[s], ab = A.absn[s], hp = A.hit_p[s];
-            float4 f0 = A.sf0[s], f1 = A.sf1[s], f2 = A.sf2[s], f3v = A.sf3[s], f4v = A.sf4[s];
             uint4 g = A.rng[s];
+#if LF_SAMPLE_REMAT
+            // the material of the hit, from the table again (GetMaterialsAndTextures, pathtrace.glsl:43-77: the same loads and the same
+            // expressions as load_surface / shade_hit, so the same bits); albedo, metallic and roughness from the path state when a texture
+            // changed them (pathtrace.glsl:82-98)
+            float4 f0 = A.sf0[s], f1, f2, f3v, f4v;
+            {
+                const float4* mp = S.materials + (size_t)7 * __float_as_int(hp.w);
+                const float4 p1 = ldg4(mp), p3 = ldg4(mp + 2), p4 = ldg4(mp + 3), p5 = ldg4(mp + 4), p6 = ldg4(mp + 5), p7 = ldg4(mp + 6);
+                f1 = p1;                                                          // albedo.xyz, specular
+                f2 = make_float4(p3.x, gmax(p3.y, 0.001f), p3.w, p4.y);           // metallic, roughness, specularTint, sheenTint
+                f3v = make_float4(p4.x, p4.z, p4.w, p5.x);                        // sheen, clearcoat, clearcoatRoughness, specTrans
+                const f3 an = -mk3(lf_log(p6.x), lf_log(p6.y), lf_log(p6.z)) / p5.z;   // the absorption below the surface (:271-272), as in shade_hit
+                f4v = make_float4(an.x, an.y, an.z, p3.z);                        // ..., subsurface
+                if (material_is_textured(S, p7.x, p7.y)) { f1 = A.sf1[s]; f2 = A.sf2[s]; }
+            }
+#else
+            float4 f0 = A.sf0[s], f1 = A.sf1[s], f2 = A.sf2[s], f3v = A.sf3[s], f4v = A.sf4[s];
+#endif
             ps.ray.d = xyz(d); ps.ray.o = mk3(0.f); ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.absn = xyz(ab);
             ps.rad = mk3(0.f); ps.stale = mk3(0.f);
             ps.rng.x = g.x; ps.rng.y = g.y; ps.rng.z = g.z; ps.rng.w = g.w;
@@ -753,7 +782,7 @@ void launch_shade(const LaunchCtx& L, int depth) {
 }
 void launch_sample(const LaunchCtx& L, int depth) {
     if (shade_is_fused(L)) return;                     // the BSDF sample ran inside the shade kernel
-    k_sample<<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.params, L.soa, L.queues, depth);
+    k_sample<<<L.sm_count * LF_SAMPLE_MINBLOCKS, 128, 0, L.stream>>>(L.scene, L.params, L.soa, L.queues, depth);
 }
 void launch_shadow(const LaunchCtx& L, int depth) {
     const Queues& Q = L.queues;

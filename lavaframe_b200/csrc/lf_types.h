@@ -88,6 +88,12 @@ struct Pair {
     T* p;
     __host__ __device__ T& operator[](size_t i) const { return p[2 * i]; }
 };
+// LF_SAMPLE_REMAT = 1 (default): k_sample re-reads the hit's material from the material table (a few records, always cached) instead of
+// being handed 4 float4 of it per path through the path state; only what a TEXTURE changed (albedo, metallic, roughness) is still handed
+// over, and only for hits on textured materials.  0 = the round-2 layout before that (sf0..sf4 always), kept for A/B runs.
+#ifndef LF_SAMPLE_REMAT
+#define LF_SAMPLE_REMAT 1
+#endif
 struct PathSoA {
     Pair<float4> ray_o;     // origin.xyz                                                           } one record
     Pair<float4> ray_d;     // direction.xyz                                                        }
@@ -95,6 +101,17 @@ struct PathSoA {
     Pair<int4>   hit_i;     // triangle ref, instance, emitter light index (-1: surface), matID    }
     Pair<float4> thr;       // throughput.xyz, bsdfSampleRec.pdf                                    } one record
     Pair<float4> rad;       // radiance.xyz                                                         }
+#if LF_SAMPLE_REMAT
+    // what k_shade hands to k_sample for a path that goes on: two full records, [sf0 | absn] and [rng | hit_p]
+    Pair<float4> sf0;       // normal.xyz, eta                                                      } one record
+    Pair<float4> absn;      // absorption.xyz                                                       }
+    Pair<uint4>  rng;       // pcg4d state                                                          } one record
+    Pair<float4> hit_p;     // first hit point (world), closest_hit.glsl:139,143; .w = material index (bits) }
+    Pair<float4> sf1;       // albedo.xyz, specular                          } one record, written and read only for hits on materials with an
+    Pair<float4> sf2;       // metallic, roughness, specularTint, sheenTint  } albedo or metallic-roughness texture
+    Pair<float4> stale;     // state.mat.emission of the last shaded surface (pathtrace.glsl:246-253 on emitter hits; scenes with lights only)  } one record
+    Pair<float4> sh_T;      // throughput the NEE sum is multiplied with (:266; fused kernel only)                                               }
+#else
     Pair<float4> absn;      // absorption.xyz                                                       } one record
     Pair<float4> stale;     // state.mat.emission of the last shaded surface (pathtrace.glsl:246-253 on emitter hits; scenes with lights only)
     Pair<uint4>  rng;       // pcg4d state                                                          } one record
@@ -106,6 +123,7 @@ struct PathSoA {
     Pair<float4> sf3;       // sheen, clearcoat, clearcoatRoughness, specTrans                      }
     Pair<float4> sf4;       // -log(extinction)/atDistance .xyz, subsurface                         } one record
     Pair<float4> sh_T;      // throughput the NEE sum is multiplied with (:266; fused kernel only)  }
+#endif
     // next-event estimation requests of the current bounce.  Candidate 0 is the environment ray when there is one, else the analytic
     // light's; candidate 1 the analytic light's when both exist (so a request with one ray touches two records, not three)
     Pair<float4> sh_o;      // surfacePos.xyz, candidate mask in .w bits (bit 0: candidate 0, bit 1: candidate 1)   } one record

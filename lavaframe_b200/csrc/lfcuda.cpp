@@ -224,7 +224,11 @@ int alloc_state(lfcuda_ctx* ctx, int tile_w, int tile_h, int frames_req) {
     PathSoA& S = ctx->soa;
     Queues& Q = ctx->queues;
     // 32-byte records of two fields each (lf_types.h Pair) + the one plain float4 array + the queues
+#if LF_SAMPLE_REMAT
+    void* rec[9] = {};
+#else
     void* rec[10] = {};
+#endif
     std::vector<Arr> arrs;
     for (void*& r : rec) arrs.push_back({&r, 32});
     arrs.push_back({(void**)&S.sh_d1, 16});
@@ -235,6 +239,14 @@ int alloc_state(lfcuda_ctx* ctx, int tile_w, int tile_h, int frames_req) {
         S.ray_o.p = lo(0); S.ray_d.p = lo(0) + 1;
         S.hit_f.p = lo(1); S.hit_i.p = (int4*)lo(1) + 1;
         S.thr.p = lo(2); S.rad.p = lo(2) + 1;
+#if LF_SAMPLE_REMAT
+        S.sf0.p = lo(3); S.absn.p = lo(3) + 1;
+        S.rng.p = (uint4*)lo(4); S.hit_p.p = lo(4) + 1;
+        S.sf1.p = lo(5); S.sf2.p = lo(5) + 1;
+        S.stale.p = lo(6); S.sh_T.p = lo(6) + 1;
+        S.sh_o.p = lo(7); S.sh_d0.p = lo(7) + 1;
+        S.sh_c0.p = lo(8); S.sh_c1.p = lo(8) + 1;
+#else
         S.absn.p = lo(3); S.stale.p = lo(3) + 1;
         S.rng.p = (uint4*)lo(4); S.hit_p.p = lo(4) + 1;
         S.sf0.p = lo(5); S.sf1.p = lo(5) + 1;
@@ -242,6 +254,7 @@ int alloc_state(lfcuda_ctx* ctx, int tile_w, int tile_h, int frames_req) {
         S.sf4.p = lo(7); S.sh_T.p = lo(7) + 1;
         S.sh_o.p = lo(8); S.sh_d0.p = lo(8) + 1;
         S.sh_c0.p = lo(9); S.sh_c1.p = lo(9) + 1;
+#endif
     };
     if (ctx->sort_rays) { arrs.push_back({(void**)&ctx->sort.sorted, 4}); arrs.push_back({(void**)&ctx->sort.keys, 4}); }
     size_t per_slot = 0;
