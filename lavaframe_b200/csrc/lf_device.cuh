@@ -748,10 +748,6 @@ LFD void load_surface(const DevScene& S, const Hit& hit, f3 rdir, Surf& s, DevCo
     const float4* tp = S.tris + (size_t)kTriStride * hit.tri;
     float4 n1 = ldg4(np), n2 = ldg4(np + 1), n3 = ldg4(np + 2);
     float bw = 1.0f - hit.u - hit.v, bu = hit.u, bv = hit.v;      // state.bary = uvt.wxy
-    float tu0 = ldg4(tp).w, tu1 = ldg4(tp + 1).w, tu2 = ldg4(tp + 2).w;   // tempTexCoords (closest_hit.glsl:141)
-    // state.texCoord = t1 * bary.x + t2 * bary.y + t3 * bary.z
-    float tcx = (tu0 * bw + tu1 * bu) + tu2 * bv;
-    float tcy = (n1.w * bw + n2.w * bu) + n3.w * bv;
     f3 normal = normalize(xyz(n1) * bw + xyz(n2) * bu + xyz(n3) * bv);
     const float4* ip = S.inst + (size_t)kInstStride * hit.inst;
     float4 m0 = ldg4(ip + 7), m1 = ldg4(ip + 8), m2 = ldg4(ip + 9);   // rows of transpose(inverse(mat3(transform)))
@@ -774,7 +770,13 @@ LFD void load_surface(const DevScene& S, const Hit& hit, f3 rdir, Surf& s, DevCo
     mat.extinction = mk3(p6.x, p6.y, p6.z);
     mat.texA = p7.x; mat.texMR = p7.y; mat.texN = p7.z; mat.texE = p7.w;
 
-    if (TEX && S.num_tex > 0) {
+    // state.texCoord is read by the four texture lookups only: its u halves sit in the triangle records (48 more bytes from a table the size of
+    // the mesh), so they are fetched for hits on materials that have a texture and for no others
+    if (TEX && S.num_tex > 0 && ((int)mat.texA >= 0 || (int)mat.texMR >= 0 || (int)mat.texN >= 0 || mat.texE >= 0)) {
+        float tu0 = ldg4(tp).w, tu1 = ldg4(tp + 1).w, tu2 = ldg4(tp + 2).w;   // tempTexCoords (closest_hit.glsl:141)
+        // state.texCoord = t1 * bary.x + t2 * bary.y + t3 * bary.z
+        float tcx = (tu0 * bw + tu1 * bu) + tu2 * bv;
+        float tcy = (n1.w * bw + n2.w * bu) + n3.w * bv;
         float tvx = tcx, tvy = 1.0f - tcy;
         if ((int)mat.texA >= 0) {
             float4 c = texArrayLinear<COUNT>(S, tvx, tvy, (int)mat.texA, cnt);
