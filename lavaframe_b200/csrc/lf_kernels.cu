@@ -72,6 +72,13 @@ LFD void load_path(const DevScene& S, const PathSoA& A, int s, int depth, PathRe
     ps.thr = xyz(th); ps.bsdf_pdf = th.w; ps.rad = xyz(ra); ps.absn = xyz(ab);
     ps.stale = LIGHTS ? xyz(A.stale[s]) : mk3(0.f);
 }
+// LF_FULL_RECORDS = 1 (experiment, off): a kernel that writes one 16-byte half of a 32-byte path-state record it has not read also writes the
+// other, unused half (zeros), on the theory that a sector written in part has to be read from DRAM first.  Measured (profiles/r2/r3d_ab_*): it does
+// not - k_generate got 25 % SLOWER with the 16 extra bytes per path (C3 19.1 -> 24.2 ms, C4 76 -> 97 ms per 8 steps), k_shade 1.5-3 % faster with
+// whole [sh_c0 | sh_c1] and [stale | sh_T] records; in total C2 +0.2 %, C3 -1.5 %, C4 -0.3 %.  Byte-masked sector writes are cheap on this GPU.
+#ifndef LF_FULL_RECORDS
+#define LF_FULL_RECORDS 0
+#endif
 // A material whose albedo or metallic / roughness come (partly) from a texture (pathtrace.glsl:82-91; the conditions of load_surface)
 LFD bool material_is_textured(const DevScene& S, float texA, float texMR) { return S.num_tex > 0 && ((int)texA >= 0 || (int)texMR >= 0); }
 // The shadow request of a surface hit.  A single candidate always goes into slot 0 of the request, whichever kind it is (with one ray the
@@ -84,6 +91,7 @@ LFD void store_nee(const PathSoA& A, int s, const Nee& nee) {
     A.sh_d0[s] = make_float4(d0.x, d0.y, d0.z, m0);
     A.sh_c0[s] = make_float4(c0.x, c0.y, c0.z, 0.f);
     if (both) { A.sh_d1[s] = make_float4(nee.d1.x, nee.d1.y, nee.d1.z, nee.m1); A.sh_c1[s] = make_float4(nee.c1.x, nee.c1.y, nee.c1.z, 0.f); }
+    else if (LF_FULL_RECORDS) A.sh_c1[s] = make_float4(0.f, 0.f, 0.f, 0.f);                   // the other half of [sh_c0 | sh_c1]
 }
 // The hit record ClosestHit left in the path state; state.fhp (closest_hit.glsl:139,143) is formed here, by full warps, instead of by the
 // few lanes of a traversal warp whose rays happen to end together - and is neither written nor re-read for paths that stop at this hit.
@@ -111,6 +119,7 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, DevParams P, PathS
             A.ray_o[s] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
             A.ray_d[s] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, 0.f);
             A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
+            if (LF_FULL_RECORDS) A.hit_p[s] = make_float4(0.f, 0.f, 0.f, 0.f);      // the other half of [rng | hit_p]; k_shade fills it in when the path goes on
             bump<COUNT>(cnt, C_SAMPLES);
         }
         queue_push(Q.active[0], count0, valid, s);
@@ -359,7 +368,10 @@ __global__ void __launch_bounds__(128, LF_SHADE_MINBLOCKS) k_shade(DevScene S, D
             A.rad[s] = make_float4(ps.rad.x, ps.rad.y, ps.rad.z, 0.f);
             if (wantSample) {
                 A.absn[s] = make_float4(ps.absn.x, ps.absn.y, ps.absn.z, 0.f);
-                if (LIGHTS) A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+                if (LIGHTS) {
+                    A.stale[s] = make_float4(ps.stale.x, ps.stale.y, ps.stale.z, 0.f);
+                    if (LF_FULL_RECORDS && LF_SAMPLE_REMAT && depth == 0) A.sh_T[s] = make_float4(0.f, 0.f, 0.f, 0.f);   // [stale | sh_T]: not read at bounce 0
+                }
                 A.rng[s] = make_uint4(ps.rng.x, ps.rng.y, ps.rng.z, ps.rng.w);
                 const Mat& m = sf.mat;
                 A.sf0[s] = make_float4(sf.normal.x, sf.normal.y, sf.normal.z, sf.eta);
